@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py - frames/s scored, ContentDetector @1080p (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps K --warmup W                  # this repo's CUDA path
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, time shards + halo
+    python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over the whole workload: `--frames` synthetic 1920x1080
+BGR24 frames per GPU (default 10 000 = 62.2 GB, far larger than L2, so no flush is needed),
+resident in HBM before the timed region.  One JSON line is printed by rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/sec scored (1080p, ContentDetector)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=10000, help="frames per GPU per step")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="steps for the host-buffer e2e leg")
+    ap.add_argument("--host-ring", type=int, default=256, help="distinct pinned host frames for e2e")
+    ap.add_argument("--cpu-sample", type=int, default=400, help="frames in the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--detector", default="content", choices=["content", "content_edges", "threshold", "histogram"])
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks / throttle sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# detector configuration per --detector
+# ------------------------------------------------------------------------------------------
+def detector_setup(kind: str):
+    from pyscenedetect_b200.detectors import ContentDetector, HistogramDetector, ThresholdDetector
+    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST
+    if kind == "content":
+        return F_HSV, (lambda: ContentDetector()), "ContentDetector() defaults: weights (1,1,1,0), threshold 27"
+    if kind == "content_edges":
+        return F_HSV | F_EDGES, (lambda: ContentDetector(weights=ContentDetector.Components(1, 1, 1, 1))), \
+            "ContentDetector(weights=(1,1,1,1))"
+    if kind == "threshold":
+        return F_BGRSUM, (lambda: ThresholdDetector()), "ThresholdDetector()"
+    return F_YHIST, (lambda: HistogramDetector(bins=256)), "HistogramDetector(bins=256)"
+
+
+def ref_detector(kind: str):
+    from oracle import ref_detectors as R
+    if kind == "content":
+        return R.RefContentDetector()
+    if kind == "content_edges":
+        return R.RefContentDetector(weights=(1.0, 1.0, 1.0, 1.0))
+    if kind == "threshold":
+        return R.RefThresholdDetector()
+    return R.RefHistogramDetector(bins=256)
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own cv2/numpy path (oracle port) on all host cores
+# ------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    kind, first, count, w, h, seed, plan_frames, steps, warmup = args
+    import cv2
+    cv2.setNumThreads(1)
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    plan = ScenePlan(plan_frames, seed=seed)
+    lo = max(0, first - 1)  # one-frame halo so the shard's first frame is scored like the serial run
+    frames = render_frames(plan.params, w, h, first=lo, count=first + count - lo)
+    times = []
+    for s in range(warmup + steps):
+        det = ref_detector(kind)
+        t0 = time.perf_counter()
+        for i in range(frames.shape[0]):
+            det.process_frame(lo + i, frames[i])
+        t1 = time.perf_counter()
+        if s >= warmup:
+            times.append(t1 - t0)
+    return times
+
+
+def run_reference(args):
+    """Time shards over all host cores, one process per core, cv2 single-threaded in each
+    (BASELINE.md §3 variant ii).  A step is a bounded sample: `cores * per_core` frames."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_core = 12
+    sample = cores * per_core
+    jobs = [(args.detector, c * per_core, per_core, args.width, args.height, args.seed,
+             max(sample, 1), args.steps, args.warmup) for c in range(cores)]
+    t0 = time.time()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    # per step: all cores run concurrently; the step ends when the slowest core ends
+    step_times = [max(r[s] for r in res) for s in range(args.steps)]
+    ms = 1000.0 * float(np.mean(step_times))
+    value = sample / (ms / 1000.0)
+    import cv2
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.detector} detector on synthetic {args.width}x{args.height} BGR24 frames "
+                               f"(seed {args.seed}); bounded sample of {sample} frames per step",
+                   "parallelism": f"{cores} processes x contiguous time shards with 1-frame halo, cv2.setNumThreads(1)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames/step ({per_core} per core) of the same synthetic 1080p sequence; "
+                                   f"oracle.ref_detectors = the reference's cv2 {cv2.__version__}/numpy {np.__version__} calls"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import ref_detectors as R  # cpu_baseline leg only (the checker, never the product path)
+    from pyscenedetect_b200 import _capi
+    from pyscenedetect_b200.engine import Engine, PinnedBuffer, synth_frames_device
+    from pyscenedetect_b200.scene_manager import SceneManager
+    from pyscenedetect_b200.synth import ScenePlan
+    from pyscenedetect_b200.video import ArrayVideoStream
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = local
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    lib = _capi.load()
+
+    W, H, N = args.width, args.height, args.frames
+    fbytes = W * H * 3
+    features, make_det, det_desc = detector_setup(args.detector)
+    total_frames = N * world
+    plan = ScenePlan(total_frames, seed=args.seed)
+    first = rank * N
+
+    # ---- resident input: this rank's contiguous time range, generated on the device ----
+    frames_t = torch.empty(N * fbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+    synth_frames_device(frames_t.data_ptr(), plan.params[first:first + N], W, H, device=dev)
+    halo_t = torch.empty(fbytes, dtype=torch.uint8, device=f"cuda:{dev}") if world > 1 else None
+    torch.cuda.synchronize()
+
+    max_batch = 2048 if not (features & 8) else 32
+    eng = Engine(W, H, features, device=dev, max_batch=max_batch)
+    weights = (1.0, 1.0, 1.0, 1.0 if args.detector == "content_edges" else 0.0)
+    sums_ptr = None
+    n_scan = N
+    d_val = torch.empty(N, dtype=torch.float64, device=f"cuda:{dev}")
+    d_comp = torch.empty(N * 4, dtype=torch.float64, device=f"cuda:{dev}")
+    d_flag = torch.empty(N, dtype=torch.uint8, device=f"cuda:{dev}")
+    wsum = float(sum(abs(x) for x in weights))
+    import ctypes as C
+    warr = (C.c_double * 4)(*weights)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        """Whole hot path for this rank's shard: halo exchange (N>1) -> fused score pass ->
+        trailing device scan.  No host sync inside."""
+        eng.reset()
+        if world > 1:
+            # ring shift of one frame over NCCL/NVLink: last frame -> rank+1, halo <- rank-1
+            ops = []
+            if rank + 1 < world:
+                ops.append(dist.P2POp(dist.isend, frames_t[(N - 1) * fbytes:], rank + 1))
+            if rank > 0:
+                ops.append(dist.P2POp(dist.irecv, halo_t, rank - 1))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+            if rank > 0:
+                torch.cuda.current_stream().synchronize()
+                eng.set_halo_device(halo_t.data_ptr())
+        eng.submit_device(frames_t.data_ptr(), N, fbytes)
+        sp, hp = eng.device_results()
+        st = eng.compute_stream  # scans are ordered after the score kernel on the engine's stream
+        if args.detector in ("content", "content_edges"):
+            _capi.check(lib.psd_scan_content(sp, N, W * H, warr, wsum, d_comp.data_ptr(), d_val.data_ptr(), st))
+            _capi.check(lib.psd_scan_compare(d_val.data_ptr(), N, 27.0, 0, d_flag.data_ptr(), st))
+        elif args.detector == "threshold":
+            _capi.check(lib.psd_scan_average(sp, N, W * H * 3, d_val.data_ptr(), st))
+        else:
+            _capi.check(lib.psd_scan_hist_correl(hp, N, 256, None, d_val.data_ptr(), st))
+
+    ext_stream = torch.cuda.ExternalStream(eng.compute_stream, device=f"cuda:{dev}")
+
+    def step_synced():
+        one_step()
+        eng.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_synced()
+    sampler = ClockSampler(dev)
+    launches0 = lib.psd_launch_count()
+    eng.timing_reset()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    ev_begin, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_begin.record(ext_stream)  # CUDA events on the stream the kernels are launched on
+    score_ms_total = 0.0
+    score_launches = 0
+    for _ in range(args.steps):
+        eng.timing_reset()
+        one_step()
+        eng.sync()
+        _tot, sc, nl = eng.timing_ms()
+        score_ms_total += sc
+        score_launches += nl
+    ev_end.record(ext_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ev_ms_total = ev_begin.elapsed_time(ev_end)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.psd_launch_count() - launches0
+    # device time per step (CUDA events on the engine's compute stream) and wall time; max over ranks
+    t = torch.tensor([ev_ms_total / args.steps, 1000.0 * wall / args.steps], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms, wall_ms = float(t[0]), float(t[1])
+    value = total_frames / (ev_ms / 1000.0)  # device-timed (CUDA events), max over ranks
+
+    # correctness spot check of what was timed (rank 0): cuts == ground-truth cuts of the plan
+    flags = d_flag.cpu().numpy() if args.detector.startswith("content") else None
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg_bytes = fbytes * N * args.steps  # per-rank algorithmic bytes through the score kernel
+        achieved = alg_bytes / (score_ms_total / 1000.0) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ev_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": f"{det_desc} on {N} synthetic {W}x{H} BGR24 frames per GPU "
+                            f"(BASELINE.json configs[1]), seed {args.seed}, full resolution",
+                "frames_per_gpu": N, "total_frames": total_frames,
+                "parallelism": f"{world} contiguous time shards, 1-frame halo over NCCL p2p" if world > 1 else "single GPU",
+                "l2": f"inputs are {N * fbytes / 1e9:.1f} GB per step per GPU, larger than L2 (126 MB): no flush needed",
+                "timed_region": "halo exchange + fused score kernel + trailing device scan, inputs resident in HBM",
+            },
+            "wall_ms_per_step": wall_ms,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "psd_score_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": fbytes,
+                "launches": int(score_launches), "avg_launch_ms": score_ms_total / max(1, score_launches),
+                "traffic": None,
+            },
+        }
+        if flags is not None:
+            line["config"]["frames_above_threshold"] = int(flags.sum())
+
+    # ---- e2e: same metric through the public API with HOST buffers (rank-local shard) ----
+    if not args.no_e2e:
+        ring = min(args.host_ring, N)
+        pin = PinnedBuffer(ring * fbytes)
+        _capi.check(lib.psd_memcpy_d2h(dev, pin.array.ctypes.data, frames_t.data_ptr(), ring * fbytes))
+        host_frames = pin.array.reshape(ring, H, W, 3)
+        e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
+        repeat = (N + ring - 1) // ring
+
+        def e2e_step():
+            sm = SceneManager(device=dev, batch_size=64)
+            sm.auto_downscale = False
+            sm.downscale = 1
+            sm.add_detector(make_det())
+            n = sm.detect_scenes(ArrayVideoStream(host_frames, 30.0, pinned=True, repeat=repeat), duration=N)
+            cuts = sm.get_cut_list()  # device->host read of the results happens inside detect_scenes
+            return n, len(cuts)
+
+        for _ in range(min(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            n_done, n_cuts = e2e_step()
+        barrier()
+        e2e_wall = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_wall], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            line["e2e"] = {
+                "value": total_frames / float(t[0]), "unit": UNIT,
+                "h2d_bytes_per_step": int(N * fbytes), "d2h_bytes_per_step": int(N * 5 * 8),
+                "steps": e2e_steps, "ms_per_step": 1000.0 * float(t[0]),
+                "api": "SceneManager.detect_scenes(ArrayVideoStream(pinned host frames)) + get_cut_list()",
+                "host_frames": f"{ring} distinct page-locked frames cycled to {N} frames per step",
+                "cuts_found": n_cuts,
+            }
+        pin.close()
+
+    # ---- cpu_baseline: oracle port (the reference's cv2/numpy calls) on the host cores, N=1 only ----
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import cv2
+        ns = min(args.cpu_sample, N)
+        sample = np.empty((ns, H, W, 3), dtype=np.uint8)
+        _capi.check(lib.psd_memcpy_d2h(dev, sample.ctypes.data, frames_t.data_ptr(), ns * fbytes))
+        det = ref_detector(args.detector)
+        for i in range(min(5, ns)):
+            det.process_frame(i, sample[i])
+        det = ref_detector(args.detector)
+        t0 = time.perf_counter()
+        for i in range(ns):
+            det.process_frame(i, sample[i])
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": ns / dt, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "port",
+            "sample": f"first {ns} frames of the same workload, single process as shipped "
+                      f"(cv2 {cv2.__version__} pool of {cv2.getNumThreads()} threads, numpy {np.__version__} single-threaded), "
+                      f"host has {os.cpu_count()} logical cores",
+            "ms_per_frame": 1000.0 * dt / ns,
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,254 @@
+// Edge component of ContentDetector (content_detector.py:213-239):
+//   median = numpy.median(V);  low/high = int(max(0,(1-s)*median)), int(min(255,(1+s)*median)), s = 1/3
+//   edges  = cv2.dilate(cv2.Canny(V, low, high), ones(k,k))
+//   delta_edges = mean |edges_t - edges_{t-1}|                       (content_detector.py:171-175)
+// Canny is restated from OpenCV's algorithm (aperture 3, L1 gradient): Sobel 3x3 with
+// BORDER_REPLICATE, fixed-point non-maximum suppression (TG22 = 13573), double threshold with
+// strict '>' and 8-connected hysteresis.  oracle/intmath.py:canny is the CPU twin pinned
+// against cv2.Canny.  Stages: thresholds (from the V histogram the score pass produced) ->
+// gradient/NMS/classify -> hysteresis to a fix-point -> separable k x k max -> SAD against the
+// previous frame's dilated map.
+#include "psd_common.cuh"
+
+namespace psd {
+
+// ---- 1. per-frame Canny thresholds from the V histogram ----
+__global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, int n, int64_t n_pixels,
+                                           int32_t* __restrict__ thr) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const uint32_t* h = vhist + (int64_t)f * 256;
+    // numpy.median: mean of the order statistics (n-1)//2 and n//2 (0-based)
+    const int64_t r_lo = (n_pixels - 1) / 2 + 1, r_hi = n_pixels / 2 + 1;
+    int lo = -1, hi = -1;
+    int64_t cum = 0;
+    for (int i = 0; i < 256; ++i) {
+        cum += h[i];
+        if (lo < 0 && cum >= r_lo) lo = i;
+        if (hi < 0 && cum >= r_hi) hi = i;
+    }
+    const double median = __ddiv_rn((double)(lo + hi), 2.0);
+    const double sigma = __ddiv_rn(1.0, 3.0);
+    const double lo_d = __dmul_rn(__dsub_rn(1.0, sigma), median);
+    const double hi_d = __dmul_rn(__dadd_rn(1.0, sigma), median);
+    int low = (int)(lo_d > 0.0 ? lo_d : 0.0);       // int(max(0, x)) truncates
+    int high = (int)(hi_d < 255.0 ? hi_d : 255.0);  // int(min(255, x))
+    if (low > high) { const int t = low; low = high; high = t; }  // cv2.Canny swaps
+    thr[2 * f] = low;
+    thr[2 * f + 1] = high;
+}
+
+// ---- 2. Sobel + L1 magnitude + NMS + double threshold ----
+constexpr int TX = 32, TY = 8;
+
+__global__ void __launch_bounds__(TX* TY) psd_canny_classify_kernel(const uint8_t* __restrict__ vplane,
+                                                                    const int32_t* __restrict__ thr,
+                                                                    uint8_t* __restrict__ map, int W,
+                                                                    int H) {
+    __shared__ uint8_t lum[TY + 4][TX + 4];
+    __shared__ int16_t sgx[TY + 2][TX + 2];
+    __shared__ int16_t sgy[TY + 2][TX + 2];
+    const int f = blockIdx.z;
+    const int64_t P = (int64_t)W * H;
+    const uint8_t* src = vplane + f * P;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    for (int i = tid; i < (TY + 4) * (TX + 4); i += TX * TY) {
+        const int ly = i / (TX + 4), lx = i - ly * (TX + 4);
+        const int gy = min(max(y0 + ly - 2, 0), H - 1), gx = min(max(x0 + lx - 2, 0), W - 1);  // replicate
+        lum[ly][lx] = src[(int64_t)gy * W + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (TY + 2) * (TX + 2); i += TX * TY) {
+        const int ly = i / (TX + 2), lx = i - ly * (TX + 2);
+        const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+        int dx = 0, dy = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            // lum index of (gy,gx) is [ly+1][lx+1]
+            const int a = lum[ly][lx], b = lum[ly][lx + 1], c = lum[ly][lx + 2];
+            const int d = lum[ly + 1][lx], e = lum[ly + 1][lx + 2];
+            const int g = lum[ly + 2][lx], h = lum[ly + 2][lx + 1], k = lum[ly + 2][lx + 2];
+            dx = (c + 2 * e + k) - (a + 2 * d + g);
+            dy = (g + 2 * h + k) - (a + 2 * b + c);
+        }
+        sgx[ly][lx] = (int16_t)dx;  // outside the image: 0 => magnitude 0
+        sgy[ly][lx] = (int16_t)dy;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int ly = threadIdx.y + 1, lx = threadIdx.x + 1;
+    auto mag = [&](int yy, int xx) { return abs((int)sgx[yy][xx]) + abs((int)sgy[yy][xx]); };
+    const int gx = sgx[ly][lx], gy = sgy[ly][lx];
+    const int m = abs(gx) + abs(gy);
+    const int low = thr[2 * f], high = thr[2 * f + 1];
+    uint8_t out = 0;
+    if (m > low) {
+        const int ax = abs(gx);
+        const int ay = abs(gy) << 15;
+        const int tg22x = ax * 13573;
+        const int tg67x = tg22x + (ax << 16);
+        bool keep;
+        if (ay < tg22x) {
+            keep = (m > mag(ly, lx - 1)) && (m >= mag(ly, lx + 1));
+        } else if (ay > tg67x) {
+            keep = (m > mag(ly - 1, lx)) && (m >= mag(ly + 1, lx));
+        } else {
+            const int s = ((gx ^ gy) < 0) ? -1 : 1;
+            keep = (m > mag(ly - 1, lx - s)) && (m > mag(ly + 1, lx + s));
+        }
+        if (keep) out = (m > high) ? 2 : 1;
+    }
+    map[f * P + (int64_t)y * W + x] = out;
+}
+
+// ---- 3. hysteresis: tile-local fix-point, repeated until no tile changes ----
+constexpr int HT = 32;  // tile edge
+
+__global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict__ map, int W, int H,
+                                                             int32_t* __restrict__ changed) {
+    __shared__ uint8_t t[HT + 2][HT + 2 + 2];
+    __shared__ int any_weak;
+    const int f = blockIdx.z;
+    const int64_t P = (int64_t)W * H;
+    uint8_t* m = map + f * P;
+    const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+    const int tid = threadIdx.x;
+    if (tid == 0) any_weak = 0;
+    __syncthreads();
+    int weak = 0;
+    for (int i = tid; i < (HT + 2) * (HT + 2); i += 256) {
+        const int ly = i / (HT + 2), lx = i - ly * (HT + 2);
+        const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = m[(int64_t)gy * W + gx];
+        t[ly][lx] = v;
+        if (v == 1 && ly >= 1 && ly <= HT && lx >= 1 && lx <= HT) weak = 1;
+    }
+    if (weak) any_weak = 1;
+    __syncthreads();
+    if (!any_weak) return;
+    volatile uint8_t(*vt)[HT + 4] = t;
+    int tile_changed = 0;
+    while (true) {
+        int ch = 0;
+        for (int i = tid; i < HT * HT; i += 256) {
+            const int ly = 1 + i / HT, lx = 1 + (i % HT);
+            if (vt[ly][lx] == 1) {
+                const bool s = vt[ly - 1][lx - 1] == 2 || vt[ly - 1][lx] == 2 || vt[ly - 1][lx + 1] == 2 ||
+                               vt[ly][lx - 1] == 2 || vt[ly][lx + 1] == 2 || vt[ly + 1][lx - 1] == 2 ||
+                               vt[ly + 1][lx] == 2 || vt[ly + 1][lx + 1] == 2;
+                if (s) {
+                    vt[ly][lx] = 2;
+                    ch = 1;
+                }
+            }
+        }
+        if (!__syncthreads_or(ch)) break;
+        tile_changed = 1;
+    }
+    if (tile_changed) {
+        for (int i = tid; i < HT * HT; i += 256) {
+            const int ly = 1 + i / HT, lx = 1 + (i % HT);
+            const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+            if (gy < H && gx < W && t[ly][lx] == 2) m[(int64_t)gy * W + gx] = 2;
+        }
+        if (tid == 0) atomicExch(changed, 1);
+    }
+}
+
+// ---- 4. dilate (separable max over k) ----
+__global__ void __launch_bounds__(256) psd_dilate_rows_kernel(const uint8_t* __restrict__ map,
+                                                              uint8_t* __restrict__ tmp, int W, int H,
+                                                              int r) {
+    const int64_t P = (int64_t)W * H;
+    const int64_t f = blockIdx.y;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const uint8_t* row = map + f * P + (int64_t)y * W;
+    uint8_t v = 0;
+    const int xa = max(x - r, 0), xb = min(x + r, W - 1);
+    for (int xx = xa; xx <= xb; ++xx) v |= (row[xx] == 2);
+    tmp[f * P + i] = v;
+}
+
+__global__ void __launch_bounds__(256) psd_dilate_cols_kernel(const uint8_t* __restrict__ tmp,
+                                                              uint8_t* __restrict__ dil, int W, int H,
+                                                              int r) {
+    const int64_t P = (int64_t)W * H;
+    const int64_t f = blockIdx.y;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const uint8_t* base = tmp + f * P;
+    uint8_t v = 0;
+    const int ya = max(y - r, 0), yb = min(y + r, H - 1);
+    for (int yy = ya; yy <= yb; ++yy) v |= base[(int64_t)yy * W + x];
+    dil[f * P + i] = v ? 255 : 0;
+}
+
+// ---- 5. SAD of dilated edge maps vs the previous frame ----
+__global__ void __launch_bounds__(256) psd_edge_sad_kernel(const uint8_t* __restrict__ dil,
+                                                           const uint8_t* __restrict__ carry,
+                                                           int64_t P, int have_prev,
+                                                           psd_frame_sums* __restrict__ sums) {
+    const int64_t f = blockIdx.y;
+    if (f == 0 && !have_prev) return;
+    const uint8_t* cur = dil + f * P;
+    const uint8_t* prv = (f == 0) ? carry : dil + (f - 1) * P;
+    uint32_t cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P;
+         i += (int64_t)gridDim.x * blockDim.x)
+        cnt += (cur[i] != prv[i]);
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    __shared__ uint32_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        if (t) atomicAdd(reinterpret_cast<unsigned long long*>(&sums[f].sad_edges), 255ull * t);
+    }
+}
+
+int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have_prev,
+                 psd_frame_sums* sums, cudaStream_t stream) {
+    PSD_REQUIRE(n > 0 && n <= 65535, "edge batch out of range");
+    const int64_t P = (int64_t)W * H;
+    psd_edge_thresholds_kernel<<<(n + 63) / 64, 64, 0, stream>>>(b.vhist, n, P, b.thresholds);
+    PSD_CHECK_LAUNCH();
+    dim3 cg((W + TX - 1) / TX, (H + TY - 1) / TY, (unsigned)n);
+    psd_canny_classify_kernel<<<cg, dim3(TX, TY), 0, stream>>>(b.vplane, b.thresholds, b.map, W, H);
+    PSD_CHECK_LAUNCH();
+    count_launch(2);
+    dim3 hg((W + HT - 1) / HT, (H + HT - 1) / HT, (unsigned)n);
+    // Each launch reaches a fix-point inside every tile; edges crossing tiles need another round.
+    for (int round = 0; round < 100000; ++round) {
+        PSD_CUDA(cudaMemsetAsync(b.changed, 0, sizeof(int32_t), stream));
+        for (int rep = 0; rep < 4; ++rep) {
+            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(b.map, W, H, b.changed);
+            PSD_CHECK_LAUNCH();
+        }
+        count_launch(4);
+        PSD_CUDA(cudaMemcpyAsync(b.changed_host, b.changed, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 stream));
+        PSD_CUDA(cudaStreamSynchronize(stream));
+        if (*b.changed_host == 0) break;
+    }
+    const int r = ksize / 2;
+    dim3 pg((unsigned)((P + 255) / 256), (unsigned)n);
+    psd_dilate_rows_kernel<<<pg, 256, 0, stream>>>(b.map, b.tmp, W, H, r);
+    PSD_CHECK_LAUNCH();
+    psd_dilate_cols_kernel<<<pg, 256, 0, stream>>>(b.tmp, b.dilated, W, H, r);
+    PSD_CHECK_LAUNCH();
+    dim3 sg((unsigned)min((int64_t)296, (P + 255) / 256), (unsigned)n);
+    psd_edge_sad_kernel<<<sg, 256, 0, stream>>>(b.dilated, b.carry, P, have_prev ? 1 : 0, sums);
+    PSD_CHECK_LAUNCH();
+    count_launch(3);
+    PSD_CUDA(cudaMemcpyAsync(b.carry, b.dilated + (int64_t)(n - 1) * P, (size_t)P,
+                             cudaMemcpyDeviceToDevice, stream));
+    return PSD_OK;
+}
+
+}  // namespace psd

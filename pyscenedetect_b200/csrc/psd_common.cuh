@@ -1,0 +1,96 @@
+// Shared helpers for the psd_b200 CUDA translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/psd_b200.h"
+
+namespace psd {
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI) ----
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define PSD_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            psd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,     \
+                           __LINE__);                                                            \
+            return (_e == cudaErrorMemoryAllocation) ? PSD_ERR_OOM : PSD_ERR_CUDA;               \
+        }                                                                                        \
+    } while (0)
+
+#define PSD_CHECK_LAUNCH()                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) {                                                                 \
+            psd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                            \
+            return PSD_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define PSD_REQUIRE(cond, ...)                                                                   \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            psd::set_error(__VA_ARGS__);                                                         \
+            return PSD_ERR_INVALID;                                                              \
+        }                                                                                        \
+    } while (0)
+
+// ---- fused score pass (score_kernel.cu) ----
+struct ScoreArgs {
+    const uint8_t* frames;   // n frames, frame_stride apart, tightly packed rows (3*W bytes)
+    const uint8_t* prev;     // predecessor of frames[0] or nullptr
+    int64_t frame_stride;
+    int32_t n_frames;
+    int32_t n_pixels;        // W*H
+    int32_t chunk_frames;    // frames per time chunk
+    int32_t n_chunks;
+    int32_t n_strips;
+    int32_t tma_ok;          // base pointers and stride 16-byte aligned
+    psd_frame_sums* sums;    // [n] (pre-zeroed)
+    uint32_t* yhist;         // [n][256] (pre-zeroed) or nullptr
+    uint32_t* vhist;         // [n][256] (pre-zeroed) or nullptr
+    uint8_t* vplane;         // [n][n_pixels] or nullptr
+};
+int launch_score(const ScoreArgs& a, uint32_t features, int variant, cudaStream_t stream);
+int score_kernel_smem_bytes();
+
+// ---- resize (resize_kernel.cu) ----
+struct ResizeTaps {  // device arrays built on the host exactly as OpenCV builds them
+    const int32_t* xofs;  // [dw] source column of tap 0
+    const int16_t* xa;    // [dw][2] 11-bit coefficients
+    const int32_t* yofs;  // [dh]
+    const int16_t* ya;    // [dh][2]
+};
+int launch_resize(const uint8_t* src, int64_t src_frame_stride, int64_t src_row_pitch, int sw, int sh,
+                  uint8_t* dst, int dw, int dh, int64_t n, const ResizeTaps& taps, cudaStream_t stream);
+
+// ---- edge path (edge_kernels.cu) ----
+struct EdgeBuffers {
+    uint8_t* vplane;    // [n][P] V of HSV (written by the score pass)
+    uint32_t* vhist;    // [n][256]
+    int32_t* thresholds;// [n][2] low, high
+    uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis 2 = edge
+    uint8_t* tmp;       // [n][P] row-dilated
+    uint8_t* dilated;   // [n][P] final dilated edges 0/255
+    uint8_t* carry;     // [P] dilated edges of the predecessor frame
+    int32_t* changed;   // device flag
+    int32_t* changed_host; // pinned
+};
+int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
+                 psd_frame_sums* sums, cudaStream_t stream);
+
+// ---- synthetic generator (synth_kernel.cu) ----
+int launch_synth(uint8_t* out, const int32_t* d_params, int64_t n, int width, int height,
+                 int64_t frame_stride, cudaStream_t stream);
+
+}  // namespace psd

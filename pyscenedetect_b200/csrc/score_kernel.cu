@@ -1,0 +1,372 @@
+// Fused per-frame score pass: one read of every BGR byte produces
+//   * SAD of the H, S, V planes against the previous frame   (content_detector.py:29-36,155,166-175)
+//   * the sum of all B,G,R bytes                              (threshold_detector.py:127)
+//   * the 256-bin histogram of YUV-Y                          (histogram_detector.py:156-159)
+//   * (edge path) the V plane + its 256-bin histogram         (content_detector.py:231,238)
+//
+// Decomposition: spatial strip x time march.  A CTA owns STRIP_PX consecutive pixels of the
+// flattened frame and walks a chunk of consecutive frames; the previous frame's H,S,V for its
+// pixels stay in registers, so HBM traffic is one read of each BGR byte (+1 halo frame per
+// chunk).  Strips are streamed global->shared by 1-D bulk TMA (cp.async.bulk + mbarrier
+// complete_tx) into a STAGES-deep ring; each thread then pulls its 16 pixels (48 B) with three
+// conflict-free LDS.128.  Per-frame partial sums go warp-shuffle -> shared atomics -> one
+// red.global.add.u64 per CTA per frame per channel, so results are order-independent integers
+// and identical for any batching / sharding.
+#include "hsv_math.cuh"
+#include "psd_common.cuh"
+
+namespace psd {
+
+constexpr int kThreads = 256;
+constexpr int kPxPerThread = 16;
+constexpr int kStripPx = kThreads * kPxPerThread;  // 4096 pixels
+constexpr int kStripBytes = kStripPx * 3;          // 12288 bytes
+constexpr int kStages = 4;
+
+struct __align__(128) ScoreSmem {
+    uint8_t ring[kStages][kStripBytes];
+    unsigned long long full[kStages];
+    int32_t sdiv[256];
+    int32_t hdiv[256];
+    uint32_t acc[2][8];        // per-frame CTA partials: sadH, sadS, sadV, bgr (double-buffered)
+    uint32_t yhist[2][256];
+    uint32_t vhist[2][256];
+};
+
+int score_kernel_smem_bytes() { return (int)sizeof(ScoreSmem); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Cooperative fallback copy for partial strips / unaligned inputs (zero-fills the tail).
+__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int valid_bytes) {
+    const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int full16 = al ? (valid_bytes >> 4) : 0;
+    for (int i = threadIdx.x; i < kStripBytes / 16; i += kThreads) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < full16) {
+            v = *reinterpret_cast<const uint4*>(src + 16 * i);
+        } else {
+            uint32_t t[4] = {0, 0, 0, 0};
+            const int base = 16 * i;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (base + k < valid_bytes) t[k >> 2] |= (uint32_t)src[base + k] << ((k & 3) * 8);
+            v = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<uint4*>(dst + 16 * i) = v;
+    }
+}
+
+template <uint32_t F, int VARIANT>
+__global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(smem_raw);
+    constexpr bool kHSV = (F & PSD_F_HSV) != 0;
+    constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
+    constexpr bool kYH = (F & PSD_F_YHIST) != 0;
+    constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x % a.n_chunks;  // chunk-fastest: concurrent CTAs hit different frames
+    const int strip = blockIdx.x / a.n_chunks;
+    const int f0 = chunk * a.chunk_frames;
+    const int nf = min(a.chunk_frames, a.n_frames - f0);
+    const int px0 = strip * kStripPx;
+    const int valid_px = min(kStripPx, a.n_pixels - px0);
+    const int valid_bytes = valid_px * 3;
+    const bool use_tma = a.tma_ok && (valid_px == kStripPx);
+
+    // iteration `it` handles frame f0 - 1 + it; it == 0 is the halo (predecessor) frame
+    const bool have_halo = kHSV && (f0 > 0 || a.prev != nullptr);
+    const int it_begin = have_halo ? 0 : 1;
+    const int it_end = nf + 1;
+    const int64_t strip_off = (int64_t)px0 * 3;
+    auto frame_ptr = [&](int it) -> const uint8_t* {
+        const int fi = f0 - 1 + it;
+        return (fi < 0 ? a.prev : a.frames + (int64_t)fi * a.frame_stride) + strip_off;
+    };
+
+    for (int i = tid; i < 256; i += kThreads) {
+        // sdiv[i] = rint((255<<12)/i), hdiv[i] = rint((180<<12)/(6i)); __double2int_rn = round-half-even
+        sm.sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
+        sm.hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
+        sm.yhist[0][i] = sm.yhist[1][i] = 0;
+        sm.vhist[0][i] = sm.vhist[1][i] = 0;
+    }
+    if (tid < 16) sm.acc[tid >> 3][tid & 7] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (use_tma && tid == 0) {
+        for (int s = 0; s < kStages && it_begin + s < it_end; ++s) {
+            mbar_expect_tx(&sm.full[s], kStripBytes);
+            bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), kStripBytes, &sm.full[s]);
+        }
+    }
+
+    Px16 prev;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
+    bool prev_valid = false;
+    const int lane = tid & 31;
+    const int my_px = px0 + tid * kPxPerThread;            // first pixel of this thread
+    const int my_valid = max(0, min(kPxPerThread, a.n_pixels - my_px));
+
+    for (int it = it_begin; it < it_end; ++it) {
+        const int k = it - it_begin;
+        const int stage = k % kStages;
+        if (use_tma) {
+            mbar_wait(&sm.full[stage], (uint32_t)((k / kStages) & 1));
+        } else {
+            coop_copy(sm.ring[stage], frame_ptr(it), valid_bytes);
+            __syncthreads();
+        }
+        uint32_t w[12];
+        {
+            const uint4* p = reinterpret_cast<const uint4*>(sm.ring[stage] + tid * 48);
+            const uint4 q0 = p[0], q1 = p[1], q2 = p[2];
+            w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+            w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+            w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+        }
+        __syncthreads();  // (A) every thread has drained this stage into registers
+        if (use_tma && tid == 0 && it + kStages < it_end) {
+            mbar_expect_tx(&sm.full[stage], kStripBytes);
+            bulk_g2s(sm.ring[stage], frame_ptr(it + kStages), kStripBytes, &sm.full[stage]);
+        }
+        // flush the previous iteration's CTA partials (complete: all warps added before (A))
+        const int fprev = f0 - 2 + it;  // frame index of iteration it-1
+        if (it > it_begin && fprev >= f0) {
+            const int slot = (it - 1) & 1;
+            if (tid < 4) {
+                const uint32_t v = sm.acc[slot][tid];
+                sm.acc[slot][tid] = 0;
+                if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fprev]) + (tid < 3 ? tid : 4),
+                                 (unsigned long long)v);
+            }
+            if (kYH) {
+                const uint32_t v = sm.yhist[slot][tid];
+                sm.yhist[slot][tid] = 0;
+                if (v) atomicAdd(&a.yhist[(int64_t)fprev * 256 + tid], v);
+            }
+            if (kEDGE) {
+                const uint32_t v = sm.vhist[slot][tid];
+                sm.vhist[slot][tid] = 0;
+                if (v) atomicAdd(&a.vhist[(int64_t)fprev * 256 + tid], v);
+            }
+        }
+
+        const int fi = f0 - 1 + it;
+        const bool own = (it >= 1);  // not the halo: this CTA accounts for this frame's own sums
+        const int slot = it & 1;
+        uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
+        if (kHSV) {
+            Px16 cur;
+            hsv16<VARIANT>(w, cur, sm.sdiv, sm.hdiv);
+            if (prev_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sad_h = __vsadu4(cur.h[j], prev.h[j]) + sad_h;
+                    sad_s = __vsadu4(cur.s[j], prev.s[j]) + sad_s;
+                    sad_v = __vsadu4(cur.v[j], prev.v[j]) + sad_v;
+                }
+            }
+            prev = cur;
+            prev_valid = true;
+            if (kEDGE && own) {
+                uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
+                if (my_valid == kPxPerThread && ((a.n_pixels & 15) == 0)) {
+                    *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
+                } else {
+                    for (int p = 0; p < my_valid; ++p) vp[p] = (uint8_t)(cur.v[p >> 2] >> ((p & 3) * 8));
+                }
+                for (int p = 0; p < my_valid; ++p)
+                    atomicAdd(&sm.vhist[slot][(cur.v[p >> 2] >> ((p & 3) * 8)) & 0xFF], 1u);
+            }
+        }
+        if (own) {
+            if (kSUM) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
+            }
+            if (kYH) {
+#pragma unroll
+                for (int p = 0; p < kPxPerThread; ++p) {
+                    if (p < my_valid) {
+                        const uint32_t y = y_px(byte_of(w, 3 * p), byte_of(w, 3 * p + 1), byte_of(w, 3 * p + 2));
+                        atomicAdd(&sm.yhist[slot][y], 1u);
+                    }
+                }
+            }
+            if (kHSV || kSUM) {
+                sad_h = __reduce_add_sync(0xFFFFFFFFu, sad_h);
+                sad_s = __reduce_add_sync(0xFFFFFFFFu, sad_s);
+                sad_v = __reduce_add_sync(0xFFFFFFFFu, sad_v);
+                bsum = __reduce_add_sync(0xFFFFFFFFu, bsum);
+                if (lane == 0) {
+                    if (kHSV) {
+                        atomicAdd(&sm.acc[slot][0], sad_h);
+                        atomicAdd(&sm.acc[slot][1], sad_s);
+                        atomicAdd(&sm.acc[slot][2], sad_v);
+                    }
+                    if (kSUM) atomicAdd(&sm.acc[slot][3], bsum);
+                }
+            }
+            if (strip == 0 && tid == 0) a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
+        }
+    }
+    __syncthreads();
+    {   // flush the last frame
+        const int fprev = f0 + nf - 1;
+        const int slot = (it_end - 1) & 1;
+        if (tid < 4) {
+            const uint32_t v = sm.acc[slot][tid];
+            if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fprev]) + (tid < 3 ? tid : 4),
+                             (unsigned long long)v);
+        }
+        if (kYH) {
+            const uint32_t v = sm.yhist[slot][tid];
+            if (v) atomicAdd(&a.yhist[(int64_t)fprev * 256 + tid], v);
+        }
+        if (kEDGE) {
+            const uint32_t v = sm.vhist[slot][tid];
+            if (v) atomicAdd(&a.vhist[(int64_t)fprev * 256 + tid], v);
+        }
+    }
+}
+
+template <uint32_t F, int VARIANT>
+static int launch_one(const ScoreArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = (int)sizeof(ScoreSmem);
+    if (!configured) {
+        PSD_CUDA(cudaFuncSetAttribute(psd_score_kernel<F, VARIANT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int64_t grid = (int64_t)a.n_chunks * a.n_strips;
+    PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
+    psd_score_kernel<F, VARIANT><<<(unsigned)grid, kThreads, smem, stream>>>(a);
+    PSD_CHECK_LAUNCH();
+    count_launch();
+    return PSD_OK;
+}
+
+template <int VARIANT>
+static int dispatch(const ScoreArgs& a, uint32_t f, cudaStream_t s) {
+    switch (f & 15u) {
+#define CASE(F) case F: return launch_one<F, VARIANT>(a, s);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+        CASE(9) CASE(11) CASE(13) CASE(15)
+#undef CASE
+        default:
+            set_error("unsupported feature mask 0x%x", f);
+            return PSD_ERR_INVALID;
+    }
+}
+
+int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStream_t stream) {
+    ScoreArgs a = a_in;
+    if (features & PSD_F_EDGES) features |= PSD_F_HSV;
+    PSD_REQUIRE(a.n_frames > 0 && a.n_pixels > 0, "empty score launch");
+    a.n_strips = (a.n_pixels + kStripPx - 1) / kStripPx;
+    if (a.chunk_frames <= 0) a.chunk_frames = 64;
+    a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.frame_stride |
+                         reinterpret_cast<uintptr_t>(a.prev);
+    a.tma_ok = ((al & 15) == 0) ? 1 : 0;
+    return variant == 0 ? dispatch<0>(a, features, stream) : dispatch<1>(a, features, stream);
+}
+
+// ---- test hook: the same device functions on a flat pixel array ----
+template <int VARIANT>
+__global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_t* h, uint8_t* s,
+                                    uint8_t* v, uint8_t* y) {
+    __shared__ int32_t sdiv[256], hdiv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
+        hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
+    }
+    __syncthreads();
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[12];
+        const uint4* p = reinterpret_cast<const uint4*>(bgr + g * 48);
+        const uint4 q0 = p[0], q1 = p[1], q2 = p[2];
+        w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+        w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+        w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+        Px16 o;
+        hsv16<VARIANT>(w, o, sdiv, hdiv);
+        *reinterpret_cast<uint4*>(h + g * 16) = make_uint4(o.h[0], o.h[1], o.h[2], o.h[3]);
+        *reinterpret_cast<uint4*>(s + g * 16) = make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]);
+        *reinterpret_cast<uint4*>(v + g * 16) = make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]);
+        for (int px = 0; px < 16; ++px)
+            y[g * 16 + px] = (uint8_t)y_px(byte_of(w, 3 * px), byte_of(w, 3 * px + 1), byte_of(w, 3 * px + 2));
+    }
+}
+
+}  // namespace psd
+
+extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixels, uint8_t* h_out,
+                            uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
+    using namespace psd;
+    PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
+    PSD_REQUIRE(variant == 0 || variant == 1, "unknown hsv variant %d", variant);
+    PSD_CUDA(cudaSetDevice(device));
+    uint8_t *d_bgr = nullptr, *d_out = nullptr;
+    PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
+    PSD_CUDA(cudaMalloc(&d_out, (size_t)n_pixels * 4));
+    PSD_CUDA(cudaMemcpy(d_bgr, bgr_host, (size_t)n_pixels * 3, cudaMemcpyHostToDevice));
+    uint8_t* dh = d_out;
+    uint8_t* ds = d_out + n_pixels;
+    uint8_t* dv = d_out + 2 * n_pixels;
+    uint8_t* dy = d_out + 3 * n_pixels;
+    if (variant == 0)
+        psd_test_hsv_kernel<0><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
+    else
+        psd_test_hsv_kernel<1><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
+    PSD_CHECK_LAUNCH();
+    count_launch();
+    PSD_CUDA(cudaDeviceSynchronize());
+    PSD_CUDA(cudaMemcpy(h_out, dh, (size_t)n_pixels, cudaMemcpyDeviceToHost));
+    PSD_CUDA(cudaMemcpy(s_out, ds, (size_t)n_pixels, cudaMemcpyDeviceToHost));
+    PSD_CUDA(cudaMemcpy(v_out, dv, (size_t)n_pixels, cudaMemcpyDeviceToHost));
+    PSD_CUDA(cudaMemcpy(y_out, dy, (size_t)n_pixels, cudaMemcpyDeviceToHost));
+    cudaFree(d_bgr);
+    cudaFree(d_out);
+    return PSD_OK;
+}

@@ -1,0 +1,8 @@
+"""GPU drop-ins for `scenedetect.detectors` (same names, constructors and metric keys)."""
+
+from .adaptive_detector import AdaptiveDetector
+from .content_detector import ContentDetector
+from .histogram_detector import HistogramDetector
+from .threshold_detector import ThresholdDetector
+
+__all__ = ["AdaptiveDetector", "ContentDetector", "HistogramDetector", "ThresholdDetector"]

@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the committed
+golden fixtures recorded from the real reference.  Integer-derived metrics are compared
+bit-exactly; `hist_diff` (cv2's SIMD summation order is not reproduced) to 1e-9, far inside
+the 1e-4 tolerance BASELINE.json states."""
+
+import hashlib
+import io
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import intmath as M
+from oracle import ref_detectors as R
+from tests.golden_util import case_frames, case_names, get_case, golden_metrics
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pyscenedetect_b200 import _capi
+    lib = _capi.load()
+    assert lib.psd_device_count() >= 1, "no CUDA device: GPU tests must run on the B200 box"
+    return lib
+
+
+def _build(case):
+    from pyscenedetect_b200.compat import FlashFilter
+    from pyscenedetect_b200.detectors import (AdaptiveDetector, ContentDetector, HistogramDetector,
+                                              ThresholdDetector)
+    kw = dict(case["kw"])
+    if "weights" in kw:
+        kw["weights"] = ContentDetector.Components(*kw["weights"])
+    if "filter_mode" in kw:
+        kw["filter_mode"] = FlashFilter.Mode[kw["filter_mode"]]
+    if "method" in kw:
+        kw["method"] = ThresholdDetector.Method[kw["method"]]
+    cls = {"content": ContentDetector, "adaptive": AdaptiveDetector, "threshold": ThresholdDetector,
+           "histogram": HistogramDetector}[case["det"]]
+    return cls(**kw)
+
+
+def _check_stats(case, stats, n):
+    from pyscenedetect_b200 import FrameTimecode
+    gold = golden_metrics(case)
+    keys = case["metric_keys"]
+    for t in range(n):
+        vals = stats.get_metrics(FrameTimecode(t, case["fps"]), keys)
+        if t not in gold:
+            assert all(v is None for v in vals), (t, vals)
+            continue
+        for k, v in zip(keys, vals):
+            want = gold[t][k]
+            if want is None:
+                assert v is None, (t, k, v)
+            elif k.startswith("hist_diff"):
+                assert abs(float(v) - want) < 1e-9, (t, k, float(v), want)
+            else:
+                assert float(v) == want, (t, k, float(v), want)
+    if not any(k.startswith("hist_diff") for k in keys):
+        buf = io.StringIO()
+        stats.save_to_csv(buf)
+        assert buf.getvalue().splitlines()[:4] == case["csv_head"]
+        assert hashlib.sha256(buf.getvalue().encode()).hexdigest() == case["csv_sha256"]
+
+
+def _scored_size(case):
+    n, w, h = case["gen"][:3]
+    if case["mode"] != "scene_manager":
+        return None
+    f = R.compute_downscale_factor(max(w, h)) if case.get("auto_downscale") else float(case.get("downscale", 1))
+    return R.downscaled_size(w, h, f) if f > 1.0 else None
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_strict_per_frame_matches_reference_golden(lib, name):
+    """detector.process_frame(timecode, frame) one frame at a time, as SceneManager drives it."""
+    from pyscenedetect_b200 import FrameTimecode, StatsManager
+    case = get_case(name)
+    frames = case_frames(case)
+    n = frames.shape[0]
+    det = _build(case)
+    stats = StatsManager() if case["stats"] else None
+    det.stats_manager = stats
+    if stats is not None:
+        stats.register_metrics(det.get_metrics())
+    det.configure(scored_size=_scored_size(case))
+    cuts = []
+    for i in range(n):
+        cuts += det.process_frame(FrameTimecode(i, case["fps"]), frames[i])
+    cuts += det.post_process(FrameTimecode(n - 1, case["fps"]))
+    assert sorted({c.frame_num for c in cuts}) == case["cuts"]
+    if stats is not None:
+        _check_stats(case, stats, n)
+    det.close()
+
+
+@pytest.mark.parametrize("batch", [7, 64])
+@pytest.mark.parametrize("name", case_names())
+def test_batched_scene_manager_matches_reference_golden(lib, name, batch):
+    """Same cases through the batched SceneManager (shared fused pass, on-device downscale)."""
+    from pyscenedetect_b200 import StatsManager
+    from pyscenedetect_b200.scene_manager import SceneManager
+    from pyscenedetect_b200.video import ArrayVideoStream
+    case = get_case(name)
+    frames = case_frames(case)
+    stats = StatsManager() if case["stats"] else None
+    sm = SceneManager(stats, batch_size=batch)
+    sm.add_detector(_build(case))
+    if case["mode"] == "scene_manager" and case.get("auto_downscale"):
+        sm.auto_downscale = True
+    else:
+        sm.auto_downscale = False
+        sm.downscale = case.get("downscale", 1)
+    total = sm.detect_scenes(ArrayVideoStream(frames, case["fps"]))
+    assert total == frames.shape[0]
+    assert [c.frame_num for c in sm.get_cut_list()] == case["cuts"]
+    if case["scene_list"] is not None:
+        assert [[a.frame_num, b.frame_num] for a, b in sm.get_scene_list()] == case["scene_list"]
+    if stats is not None:
+        _check_stats(case, stats, frames.shape[0])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_hsv_and_y_exhaustive_2_24(lib, variant):
+    """Every BGR colour through the device functions of the fused kernel vs cv2."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([(v & 255), (v >> 8) & 255, (v >> 16) & 255], axis=-1).astype(np.uint8)
+    n = img.shape[0]
+    h, s, val, y = (np.empty(n, np.uint8) for _ in range(4))
+    from pyscenedetect_b200 import _capi
+    _capi.check(lib.psd_test_hsv(0, img.ctypes.data, n, h.ctypes.data, s.ctypes.data,
+                                 val.ctypes.data, y.ctypes.data, variant))
+    want = cv2.cvtColor(img.reshape(4096, 4096, 3), cv2.COLOR_BGR2HSV).reshape(-1, 3)
+    assert np.array_equal(h, want[:, 0])
+    assert np.array_equal(s, want[:, 1])
+    assert np.array_equal(val, want[:, 2])
+    wy = cv2.cvtColor(img.reshape(4096, 4096, 3), cv2.COLOR_BGR2YUV).reshape(-1, 3)[:, 0]
+    assert np.array_equal(y, wy)
+
+
+def test_device_generator_matches_numpy(lib):
+    from pyscenedetect_b200.engine import DeviceBuffer, synth_frames_device
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    for (w, h, ns) in [(160, 90, 30), (131, 97, 29), (64, 36, 32)]:
+        plan = ScenePlan(40, seed=5, min_len=10, max_len=20, noise_shift=ns)
+        want = render_frames(plan.params, w, h)
+        buf = DeviceBuffer(want.nbytes)
+        synth_frames_device(buf.ptr, plan.params, w, h)
+        got = buf.download(want.nbytes).reshape(want.shape)
+        assert np.array_equal(got, want)
+        buf.close()
+
+
+@pytest.mark.parametrize("shape", [(160, 90), (131, 97), (17, 5), (1, 1), (4096, 3), (640, 360)])
+def test_integer_sums_any_shape(lib, shape):
+    """Raw integer outputs vs the oracle for aligned, unaligned, tiny and partial-strip sizes."""
+    from pyscenedetect_b200.engine import F_BGRSUM, F_HSV, F_YHIST, Engine
+    w, h = shape
+    rng = np.random.default_rng(w * 1000 + h)
+    frames = rng.integers(0, 256, size=(9, h, w, 3), dtype=np.uint8)
+    eng = Engine(w, h, F_HSV | F_BGRSUM | F_YHIST, max_batch=4)
+    eng.submit(frames)
+    sums = eng.read_sums()
+    hist = eng.read_yhist()
+    prev = None
+    for i, f in enumerate(frames):
+        hsv = M.bgr_to_hsv(f)
+        assert int(sums["bgr_sum"][i]) == int(f.astype(np.int64).sum())
+        assert np.array_equal(hist[i], np.bincount(M.bgr_to_y(f).ravel(), minlength=256))
+        assert int(sums["has_prev"][i]) == (1 if i else 0)
+        if prev is not None:
+            assert int(sums["sad_hue"][i]) == M.sad(hsv[0], prev[0])
+            assert int(sums["sad_sat"][i]) == M.sad(hsv[1], prev[1])
+            assert int(sums["sad_lum"][i]) == M.sad(hsv[2], prev[2])
+        prev = hsv
+    eng.close()
+
+
+def test_strided_crop_view_and_batch_invariance(lib):
+    """Non-contiguous (cropped) input views and any batching give identical integer sums."""
+    from pyscenedetect_b200.engine import F_BGRSUM, F_HSV, F_YHIST, Engine
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, size=(20, 120, 200, 3), dtype=np.uint8)
+    view = big[:, 10:100, 20:180]  # 160x90 crop, non-contiguous rows
+    ref = None
+    for batches in ([20], [1] * 20, [3, 7, 10], [19, 1]):
+        eng = Engine(160, 90, F_HSV | F_BGRSUM | F_YHIST, max_batch=8)
+        i = 0
+        for b in batches:
+            eng.submit(view[i:i + b])
+            i += b
+        got = (eng.read_sums().tobytes(), eng.read_yhist().tobytes())
+        eng.close()
+        if ref is None:
+            ref = got
+            want = Engine(160, 90, F_HSV | F_BGRSUM | F_YHIST)
+            want.submit(np.ascontiguousarray(view))
+            assert want.read_sums().tobytes() == ref[0]
+            want.close()
+        assert got == ref
+
+
+def test_halo_shards_equal_serial(lib):
+    """Contiguous time shards with a one-frame halo reproduce the serial run exactly."""
+    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    frames = render_frames(ScenePlan(60, seed=2, min_len=10, max_len=25).params, 192, 108)
+    feats = F_HSV | F_BGRSUM | F_YHIST | F_EDGES
+    serial = Engine(192, 108, feats)
+    serial.submit(frames)
+    want_s, want_h = serial.read_sums(), serial.read_yhist()
+    want_c = serial.scan_hist_correl(256)
+    for shards in (2, 3, 4):
+        bounds = [round(i * 60 / shards) for i in range(shards + 1)]
+        got_s, got_h, got_c = [], [], []
+        for r in range(shards):
+            eng = Engine(192, 108, feats)
+            if r > 0:
+                eng.set_halo(frames[bounds[r] - 1])
+            eng.submit(frames[bounds[r]:bounds[r + 1]])
+            got_s.append(eng.read_sums())
+            got_h.append(eng.read_yhist())
+            got_c.append(eng.scan_hist_correl(256))
+            eng.close()
+        assert np.concatenate(got_s).tobytes() == want_s.tobytes()
+        assert np.array_equal(np.concatenate(got_h), want_h)
+        c = np.concatenate(got_c)
+        assert np.array_equal(c[1:], want_c[1:]) and np.isnan(c[0]) and np.isnan(want_c[0])
+    serial.close()
+
+
+@pytest.mark.parametrize("src,dst", [((640, 360), (256, 144)), ((1920, 1080), (256, 144)),
+                                     ((480, 270), (160, 90)), ((131, 97), (50, 37)),
+                                     ((512, 288), (256, 144))])
+def test_device_resize_bit_exact(lib, src, dst):
+    from pyscenedetect_b200.engine import F_BGRSUM, Engine
+    rng = np.random.default_rng(src[0])
+    frames = rng.integers(0, 256, size=(3, src[1], src[0], 3), dtype=np.uint8)
+    eng = Engine(src[0], src[1], F_BGRSUM, width=dst[0], height=dst[1])
+    eng.submit(frames)
+    for i in range(3):
+        want = cv2.resize(frames[i], dst, interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(eng.debug_plane(0, i), want)
+    eng.close()
+
+
+def test_edge_intermediates_match_cv2(lib):
+    """V plane, Canny map and dilated edges of every frame vs cv2 (content_detector.py:213-239)."""
+    from pyscenedetect_b200.engine import F_EDGES, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    frames = render_frames(ScenePlan(12, seed=4, min_len=4, max_len=8).params, 320, 180)
+    rng = np.random.default_rng(0)
+    extra = np.stack([np.zeros((180, 320, 3), np.uint8), np.full((180, 320, 3), 255, np.uint8),
+                      rng.integers(0, 256, (180, 320, 3), dtype=np.uint8),
+                      cv2.GaussianBlur(rng.integers(0, 256, (180, 320, 3), dtype=np.uint8), (9, 9), 0)])
+    frames = np.concatenate([frames, extra])
+    eng = Engine(320, 180, F_EDGES, max_batch=16)
+    eng.submit(frames)
+    k = eng.edge_kernel_size
+    assert k == R.estimated_kernel_size(320, 180)
+    kernel = np.ones((k, k), np.uint8)
+    prev = None
+    sums = eng.read_sums()
+    for i, f in enumerate(frames):
+        lum = cv2.split(cv2.cvtColor(f, cv2.COLOR_BGR2HSV))[2]
+        assert np.array_equal(eng.debug_plane(1, i), lum)
+        low, high = M.canny_thresholds(float(np.median(lum)))
+        assert np.array_equal(eng.debug_plane(2, i), cv2.Canny(lum, low, high)), i
+        want = R.detect_edges(lum, kernel)
+        assert np.array_equal(eng.debug_plane(3, i), want), i
+        if prev is not None:
+            assert int(sums["sad_edges"][i]) == M.sad(want, prev)
+        prev = want
+    eng.close()
+
+
+def test_errors_are_loud(lib):
+    from pyscenedetect_b200 import FrameTimecode
+    from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector
+    from pyscenedetect_b200.engine import F_HSV, Engine
+    with pytest.raises(ValueError):
+        ContentDetector(kernel_size=4)
+    with pytest.raises(ValueError):
+        AdaptiveDetector(window_width=0)
+    with pytest.raises(ValueError):
+        HistogramDetector().process_frame(FrameTimecode(0, 30.0), np.zeros((9, 16, 3), np.float32))
+    with pytest.raises(ValueError):
+        HistogramDetector().process_frame(FrameTimecode(0, 30.0), np.zeros((9, 16, 4), np.uint8))
+    eng = Engine(16, 9, F_HSV)
+    with pytest.raises(ValueError):
+        eng.submit(np.zeros((2, 10, 16, 3), np.uint8))  # wrong size
+    with pytest.raises(ValueError):
+        eng.read_sums(0, 5)  # out of range
+    eng.close()
+    with pytest.raises(ValueError):
+        Engine(16, 9, 0)
