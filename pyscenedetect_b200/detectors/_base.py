@@ -85,6 +85,11 @@ class EngineDetector(SceneDetector):
             first = engine.frame_count - len(timecodes)
         return self._consume(list(timecodes), first)
 
+    def consume_results(self, timecodes, first: int) -> list:
+        """Run the per-frame logic over results the attached scan provider already holds
+        (frames [first, first+len(timecodes)) ) - used by the multi-GPU gather path."""
+        return self._consume(list(timecodes), first)
+
     def _validate(self, frames: np.ndarray) -> None:
         pass
 

@@ -1,0 +1,186 @@
+"""Multi-GPU time sharding: one process per GPU, contiguous frame ranges, one-frame halo.
+
+Score(t) depends only on frames t and t-1 (content_detector.py:166-175,
+histogram_detector.py:98), so rank r scores frames [bounds[r], bounds[r+1]) after receiving
+frame bounds[r]-1 from rank r-1 (a ring shift over NCCL/NVLink with the `nccl` backend, `gloo`
+in the CPU tests).  The per-frame INTEGER results are then gathered on rank 0, where the
+trailing device scans and the cut state machines run once over the whole sequence - so the
+cut list, metrics and CSV equal the serial run by construction (integer sums are
+order-independent; the float64 math happens once, in the reference's order).
+
+There is no data-path collective besides the halo send/recv and the small result gather.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from ._capi import F_YHIST, SUMS_DTYPE
+
+
+def shard_bounds(n_frames: int, world: int) -> list[int]:
+    """Contiguous, near-equal time ranges: rank r owns [b[r], b[r+1])."""
+    return [(r * n_frames) // world for r in range(world + 1)]
+
+
+class TorchComm:
+    """torch.distributed plumbing (nccl on GPUs, gloo on CPU).  Frames travel as uint8 tensors;
+    with the nccl backend they are staged through `device` memory."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cpu")
+
+    def _t(self, arr: np.ndarray):
+        return self.torch.from_numpy(np.array(arr, copy=True, order="C")).to(self.device)
+
+    def exchange_halo(self, last_frame: np.ndarray | None, shape) -> np.ndarray | None:
+        """Send my last frame to rank+1, receive rank-1's last frame (None on rank 0)."""
+        dist, torch = self.dist, self.torch
+        ops, recv = [], None
+        if self.rank + 1 < self.world:
+            assert last_frame is not None
+            ops.append(dist.P2POp(dist.isend, self._t(last_frame), self.rank + 1))
+        if self.rank > 0:
+            recv = torch.empty(tuple(shape), dtype=torch.uint8, device=self.device)
+            ops.append(dist.P2POp(dist.irecv, recv, self.rank - 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if recv is None:
+            return None
+        if recv.is_cuda:
+            torch.cuda.synchronize()
+        return recv.cpu().numpy()
+
+    def gather_rows(self, rows: np.ndarray, counts: list[int]) -> np.ndarray | None:
+        """Concatenate per-rank row blocks (raw bytes) on rank 0; other ranks get None."""
+        dist, torch = self.dist, self.torch
+        row_bytes = rows.dtype.itemsize * int(np.prod(rows.shape[1:], dtype=np.int64))
+        cap = max(counts) * row_bytes
+        buf = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+        raw = np.frombuffer(np.ascontiguousarray(rows).tobytes(), dtype=np.uint8)
+        buf[: raw.size] = self._t(raw)
+        outs = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(outs, buf)
+        if self.rank != 0:
+            return None
+        parts = []
+        for r, o in enumerate(outs):
+            b = o[: counts[r] * row_bytes].cpu().numpy().tobytes()
+            parts.append(np.frombuffer(b, dtype=rows.dtype).reshape((counts[r],) + rows.shape[1:]))
+        return np.concatenate(parts)
+
+
+class GatheredResults:
+    """Scan provider over gathered integer results: presents the `Engine.scan_*` interface the
+    detectors consume, backed by the stateless device scans of the C-ABI (psd_scan_*)."""
+
+    def __init__(self, sums: np.ndarray, yhist: np.ndarray | None, n_pixels: int, device: int = 0):
+        import ctypes as C
+
+        from . import _capi
+        from .engine import DeviceBuffer
+        self._C, self._capi = C, _capi
+        self._lib = _capi.load()
+        self.device = device
+        self.n_pixels = int(n_pixels)
+        self._n = int(sums.shape[0])
+        self._sums = DeviceBuffer(max(1, sums.nbytes), device)
+        self._sums.upload(sums.view(np.uint8).reshape(-1))
+        self._hist = None
+        if yhist is not None:
+            self._hist = DeviceBuffer(max(1, yhist.nbytes), device)
+            self._hist.upload(np.ascontiguousarray(yhist).view(np.uint8).reshape(-1))
+        self._DeviceBuffer = DeviceBuffer
+
+    @property
+    def frame_count(self) -> int:
+        return self._n
+
+    def _out(self, count: int):
+        return self._DeviceBuffer(max(8, count * 8), self.device)
+
+    def _fetch(self, buf, count: int) -> np.ndarray:
+        return buf.download(count * 8).view(np.float64).copy()
+
+    def scan_content(self, weights, first: int = 0, n: int | None = None):
+        n = self._n - first if n is None else n
+        w = (self._C.c_double * 4)(*[float(x) for x in weights])
+        wsum = float(sum(abs(x) for x in weights))
+        val, comps = self._out(n), self._out(4 * n)
+        self._capi.check(self._lib.psd_scan_content(self._sums.ptr + first * 64, n, self.n_pixels, w, wsum,
+                                                    comps.ptr, val.ptr, None), "psd_scan_content")
+        return self._fetch(val, n), self._fetch(comps, 4 * n).reshape(n, 4)
+
+    def scan_adaptive(self, scores: np.ndarray, window_width: int, min_content_val: float) -> np.ndarray:
+        s = np.ascontiguousarray(scores, dtype=np.float64)
+        n = s.shape[0]
+        inp, out = self._out(n), self._out(n)
+        inp.upload(s.view(np.uint8))
+        self._capi.check(self._lib.psd_scan_adaptive(inp.ptr, n, int(window_width), float(min_content_val),
+                                                     out.ptr, None), "psd_scan_adaptive")
+        return self._fetch(out, n)
+
+    def scan_average(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self._n - first if n is None else n
+        out = self._out(n)
+        self._capi.check(self._lib.psd_scan_average(self._sums.ptr + first * 64, n, self.n_pixels * 3,
+                                                    out.ptr, None), "psd_scan_average")
+        return self._fetch(out, n)
+
+    def scan_hist_correl(self, bins: int, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self._n - first if n is None else n
+        out = self._out(n)
+        prev = self._hist.ptr + (first - 1) * 1024 if first > 0 else None
+        self._capi.check(self._lib.psd_scan_hist_correl(self._hist.ptr + first * 1024, n, int(bins), prev,
+                                                        out.ptr, None), "psd_scan_hist_correl")
+        return self._fetch(out, n)
+
+
+def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int, detector, fps,
+                   comm, engine_factory=None, results_factory=None, batch_size: int = 64):
+    """Run `detector` over a sequence that is split across ranks by contiguous time range.
+
+    frames_local: this rank's frames (n_local,H,W,3) = global frames [first_index, first_index+n_local).
+    Returns (cut_frame_numbers, gathered_sums) on rank 0 and (None, None) elsewhere.
+    `engine_factory` / `results_factory` exist so the CPU tests can substitute oracle-backed
+    scorers; the defaults are the CUDA engine and the C-ABI device scans.
+    """
+    from .compat import FrameTimecode
+    if engine_factory is None:
+        from .engine import Engine as engine_factory  # noqa: N813
+    if results_factory is None:
+        results_factory = GatheredResults
+    n_local, h, w = frames_local.shape[0], frames_local.shape[1], frames_local.shape[2]
+    features = detector.required_features()
+    eng = engine_factory(w, h, features, max_batch=batch_size,
+                         edge_kernel_size=detector.edge_kernel_size_arg())
+    halo = comm.exchange_halo(frames_local[-1] if n_local else None, (h, w, 3))
+    if halo is not None:
+        eng.set_halo(halo)
+    for i in range(0, n_local, batch_size):
+        eng.submit(frames_local[i:i + batch_size])
+    sums = eng.read_sums()
+    yh = eng.read_yhist() if features & F_YHIST else None
+    counts = [b - a for a, b in zip(shard_bounds(total_frames, comm.world)[:-1],
+                                    shard_bounds(total_frames, comm.world)[1:])]
+    assert counts[comm.rank] == n_local and shard_bounds(total_frames, comm.world)[comm.rank] == first_index
+    all_sums = comm.gather_rows(sums, counts)
+    all_hist = comm.gather_rows(yh, counts) if yh is not None else None
+    eng.close()
+    if comm.rank != 0:
+        return None, None
+    assert all_sums.dtype == SUMS_DTYPE and all_sums.shape[0] == total_frames
+    res = results_factory(all_sums, all_hist, w * h)
+    detector.attach_engine(res)
+    detector._base_index = 0
+    tcs = [FrameTimecode(i, fps) for i in range(total_frames)]
+    cuts = []
+    for i in range(0, total_frames, 4096):
+        cuts += detector.consume_results(tcs[i:i + 4096], i)
+    cuts += detector.post_process(tcs[-1])
+    return sorted({c.frame_num for c in cuts}), all_sums

@@ -128,3 +128,17 @@ class OracleEngine:
             b = M.hist_normalize_l2(rebin(self._hist[t]))
             out[i] = M.hist_correl(a, b)
         return out
+
+
+class OracleResults(OracleEngine):
+    """`GatheredResults` stand-in: the scans of OracleEngine over gathered integer arrays."""
+
+    def __init__(self, sums, yhist, n_pixels, device=0):
+        self.n_pixels = int(n_pixels)
+        self._sums = list(sums)
+        self._hist = list(yhist) if yhist is not None else []
+        self._halo_hist = None
+
+    def read_sums(self, first=0, n=None):
+        n = self.frame_count - first if n is None else n
+        return np.array(self._sums[first:first + n], dtype=SUMS_DTYPE)
