@@ -305,7 +305,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
     e->features = cfg->features | ((cfg->features & PSD_F_EDGES) ? PSD_F_HSV : 0);
     e->max_batch = cfg->max_batch;
     e->variant = 1;
-    if (const char* v = getenv("PSD_HSV_VARIANT")) e->variant = atoi(v) ? 1 : 0;
+    if (const char* v = getenv("PSD_HSV_VARIANT")) e->variant = atoi(v);
     if (e->features & PSD_F_EDGES) {
         int k = cfg->edge_kernel_size;
         if (k == 0) {  // content_detector.py:39-46; Python round() is half-to-even like nearbyint

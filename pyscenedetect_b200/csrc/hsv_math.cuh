@@ -81,6 +81,239 @@ __device__ __forceinline__ void hsv_px_rcp(uint32_t b, uint32_t g, uint32_t r, u
     V = (uint32_t)v;
 }
 
+// ---- variant 2: float-domain pipeline on pixel PAIRS with packed FFMA2/FADD2 (sm_100 f32x2) ----
+// Bytes are lifted to "magic" floats 2^23 + b by one PRMT each (mantissa ulp = 1, so integer
+// add/sub/compare on them is exact and order-preserving).  The table values are regenerated as in
+// variant 1; the two fixed-point products use directed rounding so that only bits below the
+// 4096 quantum are dropped before the >> 12:
+//   S:  x = fma.rz(d, sdiv, 2048)  (x >= 0: truncation never crosses a multiple of 4096)
+//       y = fma.rz(x, 2^-12, 2^23)            -> mantissa = floor(x / 4096) = S
+//   H:  x = fma.rm(h, hdiv, 2048)  (h may be negative: round toward -inf == arithmetic shift)
+//       y = fma.rm(x, 2^-12, 1.5 * 2^23)      -> mantissa = 2^22 + floor(x / 4096)
+// |d * sdiv| < 2^28 and |h * hdiv| < 2^25, so the dropped bits are at most 2^4 resp. 2^1 wide and
+// 4096 k is always representable: floor(x/4096) is unchanged.  Pinned by the exhaustive test.
+typedef unsigned long long f32x2_t;
+
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2_rz(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2_rm(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// byte j of word w -> float 2^23 + byte  (PRMT with the constant 0x4B000000 as second source)
+template <int J>
+__device__ __forceinline__ float magic_byte(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | J));
+}
+
+struct PairOut {  // H, S, V of two pixels as magic-float bit patterns (value in the low byte)
+    uint32_t h0, h1, s0, s1, v0, v1;
+};
+
+// bytes of pixels (P, P+1) inside the 12 packed words: pixel p occupies bytes 3p, 3p+1, 3p+2
+template <int P>
+__device__ __forceinline__ void hsv_pair_f32x2(const uint32_t (&w)[12], PairOut& o) {
+    constexpr int kb0 = 3 * P, kb1 = 3 * P + 3;
+    const float B0 = magic_byte<(kb0 + 0) & 3>(w[(kb0 + 0) >> 2]);
+    const float G0 = magic_byte<(kb0 + 1) & 3>(w[(kb0 + 1) >> 2]);
+    const float R0 = magic_byte<(kb0 + 2) & 3>(w[(kb0 + 2) >> 2]);
+    const float B1 = magic_byte<(kb1 + 0) & 3>(w[(kb1 + 0) >> 2]);
+    const float G1 = magic_byte<(kb1 + 1) & 3>(w[(kb1 + 1) >> 2]);
+    const float R1 = magic_byte<(kb1 + 2) & 3>(w[(kb1 + 2) >> 2]);
+    // max / min on the bit patterns (order-preserving for these positive floats)
+    const uint32_t V0 = __vimax3_u32(__float_as_uint(B0), __float_as_uint(G0), __float_as_uint(R0));
+    const uint32_t V1 = __vimax3_u32(__float_as_uint(B1), __float_as_uint(G1), __float_as_uint(R1));
+    const uint32_t m0 = __vimin3_u32(__float_as_uint(B0), __float_as_uint(G0), __float_as_uint(R0));
+    const uint32_t m1 = __vimin3_u32(__float_as_uint(B1), __float_as_uint(G1), __float_as_uint(R1));
+    const f32x2_t Vm = pack2(__uint_as_float(V0), __uint_as_float(V1));
+    const f32x2_t mn = pack2(__uint_as_float(m0), __uint_as_float(m1));
+    const f32x2_t d2 = sub2(Vm, mn);  // plain floats 0..255 (exact)
+    float d0, d1;
+    unpack2(d2, d0, d1);
+    // reciprocals of max(V,1), max(d,1): d == 0 whenever V == 0, and h == 0 whenever d == 0, so the
+    // clamped entries are multiplied by zero exactly as the tables' zero entries would be
+    const f32x2_t M23 = pack2(8388608.0f, 8388608.0f);
+    const f32x2_t M15 = pack2(12582912.0f, 12582912.0f);
+    const f32x2_t Vg = pack2(__uint_as_float(max(V0, 0x4B000001u)), __uint_as_float(max(V1, 0x4B000001u)));
+    float Vp0, Vp1;
+    unpack2(sub2(Vg, M23), Vp0, Vp1);
+    const f32x2_t rV = pack2(rcp_approx(Vp0), rcp_approx(Vp1));
+    const f32x2_t rd = pack2(rcp_approx(fmaxf(d0, 1.0f)), rcp_approx(fmaxf(d1, 1.0f)));
+    const f32x2_t sdiv = sub2(fma2_rn(pack2(1044480.0f, 1044480.0f), rV, M15), M15);
+    const f32x2_t hdiv = sub2(fma2_rn(pack2(122880.0f, 122880.0f), rd, M15), M15);
+    const f32x2_t c2048 = pack2(2048.0f, 2048.0f);
+    const f32x2_t cshift = pack2(0.000244140625f, 0.000244140625f);  // 2^-12
+    const f32x2_t ys = fma2_rz(fma2_rz(d2, sdiv, c2048), cshift, M23);
+    // hue numerators (differences of magic floats are exact small integers)
+    const f32x2_t B2 = pack2(B0, B1), G2 = pack2(G0, G1), R2 = pack2(R0, R1);
+    const f32x2_t hR = sub2(G2, B2);
+    const f32x2_t hG = fma2_rn(d2, pack2(2.0f, 2.0f), sub2(B2, R2));
+    const f32x2_t hB = fma2_rn(d2, pack2(4.0f, 4.0f), sub2(R2, G2));
+    float hR0, hR1, hG0, hG1, hB0, hB1;
+    unpack2(hR, hR0, hR1);
+    unpack2(hG, hG0, hG1);
+    unpack2(hB, hB0, hB1);
+    const float h0 = (V0 == __float_as_uint(R0)) ? hR0 : ((V0 == __float_as_uint(G0)) ? hG0 : hB0);
+    const float h1 = (V1 == __float_as_uint(R1)) ? hR1 : ((V1 == __float_as_uint(G1)) ? hG1 : hB1);
+    float yh0, yh1;
+    unpack2(fma2_rm(fma2_rm(pack2(h0, h1), hdiv, c2048), cshift, M15), yh0, yh1);
+    if (yh0 < 12582912.0f) yh0 += 180.0f;
+    if (yh1 < 12582912.0f) yh1 += 180.0f;
+    float ys0, ys1;
+    unpack2(ys, ys0, ys1);
+    o.h0 = __float_as_uint(yh0); o.h1 = __float_as_uint(yh1);
+    o.s0 = __float_as_uint(ys0); o.s1 = __float_as_uint(ys1);
+    o.v0 = V0; o.v1 = V1;
+}
+
+// four magic words (value in the low byte) -> one planar word; the two IMADs run on the FMA pipe
+__device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = b * 256u + a;  // low 16 bits = [a.b0, b.b0] (a's upper bytes only reach bytes 2,3)
+    const uint32_t hi = d * 256u + c;
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+__device__ __forceinline__ void hsv16_f32x2(const uint32_t (&w)[12], Px16& o) {
+    PairOut p[8];
+    hsv_pair_f32x2<0>(w, p[0]);
+    hsv_pair_f32x2<2>(w, p[1]);
+    hsv_pair_f32x2<4>(w, p[2]);
+    hsv_pair_f32x2<6>(w, p[3]);
+    hsv_pair_f32x2<8>(w, p[4]);
+    hsv_pair_f32x2<10>(w, p[5]);
+    hsv_pair_f32x2<12>(w, p[6]);
+    hsv_pair_f32x2<14>(w, p[7]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o.h[j] = pack4_low_bytes(p[2 * j].h0, p[2 * j].h1, p[2 * j + 1].h0, p[2 * j + 1].h1);
+        o.s[j] = pack4_low_bytes(p[2 * j].s0, p[2 * j].s1, p[2 * j + 1].s0, p[2 * j + 1].s1);
+        o.v[j] = pack4_low_bytes(p[2 * j].v0, p[2 * j].v1, p[2 * j + 1].v0, p[2 * j + 1].v1);
+    }
+}
+
+// ---- variant 3: variant 2 re-balanced for the measured B200 pipes (profiles/r01_pipes.md):
+// the ALU pipe (PRMT/VIMNMX/ISETP/SEL/FMNMX) issues at half the rate of the FMA pipe, so every
+// step that can run on the FMA pipe is moved there:
+//   * divide-by-zero guards: rcp(x + 2^-24) instead of rcp(max(x,1)); for x >= 1 the sum rounds
+//     back to x, for x == 0 the huge-but-finite reciprocal is multiplied by d == 0 / h == 0;
+//   * hue sector: instead of two compares and two selects, every candidate gets the penalty
+//     4096 * (V - channel) (zero only for a channel that attains the max) and one 3-input
+//     minimum picks the winner; ties between channels give the same H as OpenCV's R > G > B
+//     priority for all 2^24 colours (checked exhaustively on the CPU and on the device);
+//   * H < 0 -> H + 180 with a saturating add: m = sat(1.5*2^23 - y) is 1 exactly when the
+//     integer H is negative, then y += 180 m. ----
+__device__ __forceinline__ float fadd_sat(float a, float b) {
+    float r;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+template <int P>
+__device__ __forceinline__ void hsv_pair_v3(const uint32_t (&w)[12], PairOut& o) {
+    constexpr int kb0 = 3 * P, kb1 = 3 * P + 3;
+    const float B0 = magic_byte<(kb0 + 0) & 3>(w[(kb0 + 0) >> 2]);
+    const float G0 = magic_byte<(kb0 + 1) & 3>(w[(kb0 + 1) >> 2]);
+    const float R0 = magic_byte<(kb0 + 2) & 3>(w[(kb0 + 2) >> 2]);
+    const float B1 = magic_byte<(kb1 + 0) & 3>(w[(kb1 + 0) >> 2]);
+    const float G1 = magic_byte<(kb1 + 1) & 3>(w[(kb1 + 1) >> 2]);
+    const float R1 = magic_byte<(kb1 + 2) & 3>(w[(kb1 + 2) >> 2]);
+    const uint32_t V0 = __vimax3_u32(__float_as_uint(B0), __float_as_uint(G0), __float_as_uint(R0));
+    const uint32_t V1 = __vimax3_u32(__float_as_uint(B1), __float_as_uint(G1), __float_as_uint(R1));
+    const uint32_t m0 = __vimin3_u32(__float_as_uint(B0), __float_as_uint(G0), __float_as_uint(R0));
+    const uint32_t m1 = __vimin3_u32(__float_as_uint(B1), __float_as_uint(G1), __float_as_uint(R1));
+    const f32x2_t Vm = pack2(__uint_as_float(V0), __uint_as_float(V1));
+    const f32x2_t mn = pack2(__uint_as_float(m0), __uint_as_float(m1));
+    const f32x2_t M23 = pack2(8388608.0f, 8388608.0f);
+    const f32x2_t M15 = pack2(12582912.0f, 12582912.0f);
+    const f32x2_t eps = pack2(5.9604644775390625e-8f, 5.9604644775390625e-8f);  // 2^-24
+    const f32x2_t d2 = sub2(Vm, mn);
+    float dg0, dg1, Vg0, Vg1;
+    unpack2(add2(d2, eps), dg0, dg1);
+    unpack2(add2(sub2(Vm, M23), eps), Vg0, Vg1);
+    const f32x2_t rV = pack2(rcp_approx(Vg0), rcp_approx(Vg1));
+    const f32x2_t rd = pack2(rcp_approx(dg0), rcp_approx(dg1));
+    const f32x2_t sdiv = sub2(fma2_rn(pack2(1044480.0f, 1044480.0f), rV, M15), M15);
+    const f32x2_t hdiv = sub2(fma2_rn(pack2(122880.0f, 122880.0f), rd, M15), M15);
+    const f32x2_t c2048 = pack2(2048.0f, 2048.0f);
+    const f32x2_t cshift = pack2(0.000244140625f, 0.000244140625f);  // 2^-12
+    const f32x2_t ys = fma2_rz(fma2_rz(d2, sdiv, c2048), cshift, M23);
+    const f32x2_t B2 = pack2(B0, B1), G2 = pack2(G0, G1), R2 = pack2(R0, R1);
+    const f32x2_t K = pack2(4096.0f, 4096.0f);
+    // candidate + 4096 * (V - channel)
+    const f32x2_t hR = fma2_rn(sub2(Vm, R2), K, sub2(G2, B2));
+    const f32x2_t hG = fma2_rn(sub2(Vm, G2), K, fma2_rn(d2, pack2(2.0f, 2.0f), sub2(B2, R2)));
+    const f32x2_t hB = fma2_rn(sub2(Vm, B2), K, fma2_rn(d2, pack2(4.0f, 4.0f), sub2(R2, G2)));
+    float hR0, hR1, hG0, hG1, hB0, hB1;
+    unpack2(hR, hR0, hR1);
+    unpack2(hG, hG0, hG1);
+    unpack2(hB, hB0, hB1);
+    const f32x2_t h2 = pack2(fmin3(hR0, hG0, hB0), fmin3(hR1, hG1, hB1));
+    float yh0, yh1;
+    unpack2(fma2_rm(fma2_rm(h2, hdiv, c2048), cshift, M15), yh0, yh1);
+    yh0 = fmaf(fadd_sat(12582912.0f, -yh0), 180.0f, yh0);
+    yh1 = fmaf(fadd_sat(12582912.0f, -yh1), 180.0f, yh1);
+    float ys0, ys1;
+    unpack2(ys, ys0, ys1);
+    o.h0 = __float_as_uint(yh0); o.h1 = __float_as_uint(yh1);
+    o.s0 = __float_as_uint(ys0); o.s1 = __float_as_uint(ys1);
+    o.v0 = V0; o.v1 = V1;
+}
+
+__device__ __forceinline__ void hsv16_v3(const uint32_t (&w)[12], Px16& o) {
+    PairOut p[8];
+    hsv_pair_v3<0>(w, p[0]);
+    hsv_pair_v3<2>(w, p[1]);
+    hsv_pair_v3<4>(w, p[2]);
+    hsv_pair_v3<6>(w, p[3]);
+    hsv_pair_v3<8>(w, p[4]);
+    hsv_pair_v3<10>(w, p[5]);
+    hsv_pair_v3<12>(w, p[6]);
+    hsv_pair_v3<14>(w, p[7]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o.h[j] = pack4_low_bytes(p[2 * j].h0, p[2 * j].h1, p[2 * j + 1].h0, p[2 * j + 1].h1);
+        o.s[j] = pack4_low_bytes(p[2 * j].s0, p[2 * j].s1, p[2 * j + 1].s0, p[2 * j + 1].s1);
+        o.v[j] = pack4_low_bytes(p[2 * j].v0, p[2 * j].v1, p[2 * j + 1].v0, p[2 * j + 1].v1);
+    }
+}
+
 __device__ __forceinline__ uint32_t y_px(uint32_t b, uint32_t g, uint32_t r) {
     return (r * 4899u + g * 9617u + b * 1868u + 8192u) >> 14;
 }
@@ -90,9 +323,20 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[12], int k) {
     return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
 }
 
+__device__ __forceinline__ void hsv16_f32x2(const uint32_t (&w)[12], Px16& o);
+__device__ __forceinline__ void hsv16_v3(const uint32_t (&w)[12], Px16& o);
+
 template <int VARIANT>
 __device__ __forceinline__ void hsv16(const uint32_t (&w)[12], Px16& o, const int32_t* sdiv,
                                       const int32_t* hdiv) {
+    if (VARIANT == 2) {
+        hsv16_f32x2(w, o);
+        return;
+    }
+    if (VARIANT == 3) {
+        hsv16_v3(w, o);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t hw = 0, sw = 0, vw = 0;

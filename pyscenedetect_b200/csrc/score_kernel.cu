@@ -308,7 +308,13 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.frame_stride |
                          reinterpret_cast<uintptr_t>(a.prev);
     a.tma_ok = ((al & 15) == 0) ? 1 : 0;
-    return variant == 0 ? dispatch<0>(a, features, stream) : dispatch<1>(a, features, stream);
+    PSD_REQUIRE(variant >= 0 && variant <= 3, "unknown hsv variant %d", variant);
+    switch (variant) {
+        case 0: return dispatch<0>(a, features, stream);
+        case 1: return dispatch<1>(a, features, stream);
+        case 2: return dispatch<2>(a, features, stream);
+        default: return dispatch<3>(a, features, stream);
+    }
 }
 
 // ---- test hook: the same device functions on a flat pixel array ----
@@ -345,7 +351,7 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
                             uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
     using namespace psd;
     PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
-    PSD_REQUIRE(variant == 0 || variant == 1, "unknown hsv variant %d", variant);
+    PSD_REQUIRE(variant >= 0 && variant <= 3, "unknown hsv variant %d", variant);
     PSD_CUDA(cudaSetDevice(device));
     uint8_t *d_bgr = nullptr, *d_out = nullptr;
     PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
@@ -357,8 +363,12 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
     uint8_t* dy = d_out + 3 * n_pixels;
     if (variant == 0)
         psd_test_hsv_kernel<0><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
-    else
+    else if (variant == 1)
         psd_test_hsv_kernel<1><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
+    else if (variant == 2)
+        psd_test_hsv_kernel<2><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
+    else
+        psd_test_hsv_kernel<3><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
     PSD_CHECK_LAUNCH();
     count_launch();
     PSD_CUDA(cudaDeviceSynchronize());

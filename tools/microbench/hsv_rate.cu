@@ -1,0 +1,73 @@
+// Compute-only rate of the per-pixel HSV + SAD arithmetic (no memory traffic): how many pixels
+// per clock per SM can each formulation in csrc/hsv_math.cuh retire?  The fused kernel needs
+// 2.18 Tpx/s for 100 % of the measured HBM roofline = 7.5 px/clk/SM at 1.965 GHz on 148 SMs.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hsv_rate hsv_rate.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../pyscenedetect_b200/csrc/hsv_math.cuh"
+
+using namespace psd;
+constexpr int ITERS = 2048;
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 3) rate_kernel(uint32_t* out, uint32_t seed, long long* cyc) {
+    __shared__ int32_t sdiv[256], hdiv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
+        hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
+    }
+    __syncthreads();
+    uint32_t w[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = seed * (j + 1) + threadIdx.x * 2654435761u;
+    Px16 prev;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
+    uint32_t sh = 0, ss = 0, sv = 0;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        Px16 cur;
+        hsv16<VARIANT>(w, cur, sdiv, hdiv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sh = __vsadu4(cur.h[j], prev.h[j]) + sh;
+            ss = __vsadu4(cur.s[j], prev.s[j]) + ss;
+            sv = __vsadu4(cur.v[j], prev.v[j]) + sv;
+        }
+        prev = cur;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) w[j] += 0x9E3779B9u + j;  // 12 IADD per 16 px of input churn
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sh ^ ss ^ sv;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int VARIANT>
+void run(uint32_t* out, long long* cyc) {
+    const int grid = 148 * 3;
+    rate_kernel<VARIANT><<<grid, 256>>>(out, 12345u, cyc);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    rate_kernel<VARIANT><<<grid, 256>>>(out, 12345u, cyc);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double px = (double)grid * 256 * 16 * ITERS;
+    printf("variant %d: %8.3f Gpx/s  (%.3f ms)  = %.2f %% of the 2180 Gpx/s HBM-roofline pixel rate %s\n", VARIANT,
+           px / ms / 1e6, ms, 100.0 * px / ms / 1e6 / 2180.0, err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+int main() {
+    uint32_t* out; long long* cyc;
+    cudaMalloc(&out, 148 * 3 * 256 * 4); cudaMalloc(&cyc, 148 * 3 * 8);
+    run<0>(out, cyc);
+    run<1>(out, cyc);
+    run<2>(out, cyc);
+    run<3>(out, cyc);
+    return 0;
+}
