@@ -314,6 +314,127 @@ __device__ __forceinline__ void hsv16_v3(const uint32_t (&w)[12], Px16& o) {
     }
 }
 
+// ---- variant 4: fewest lane-operations (the measured B200 model is "one 32-lane operation per
+// clock per SM sub-partition", with IMAD/IDP4A confined to one 16-lane half and
+// PRMT/LOP3/SHF/VIMNMX to the other - profiles/r01_pipes_microbench.txt).
+//   * the two tables come back as a conflict-free shared-memory LUT, but pre-divided by 4096 and
+//     stored as float, replicated per lane (row i = 32 x sdiv[i]/4096 | 32 x hdiv[i]/4096, 256 B),
+//     so a lookup is one IMAD (address = value * 256 + lane offset; the 2^23 magic exponent
+//     overflows out of the 32-bit product) and one LDS;
+//   * S and H are then ONE directed-rounding FMA each: with the magic constant 2^15 (ulp 2^-8) the
+//     +0.5 of the fixed-point rounding is representable, and the integer part of
+//     d*sdiv/4096 + 0.5 lands byte-aligned in bits 8..15 of the result:
+//       yS = fma.rz(d, sdiv/4096, 32768.5)          -> byte 1 = S
+//       yH = fma.rm(h, hdiv/4096, 49152.5)          -> byte 1 = H mod 256, H < 0 <=> yH < 49152
+//   * bytes are lifted to magic floats with IDP4A (A half) instead of PRMT (B half). ----
+struct LutView {
+    uint32_t s_addr;  // shared-window byte address of this lane's sdiv column
+    uint32_t h_addr;  // ... of this lane's hdiv column
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_rz(float a, float b, float c) {
+    float r;
+    asm("fma.rz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_rm(float a, float b, float c) {
+    float r;
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+template <int J>
+__device__ __forceinline__ float magic_byte_dp4a(uint32_t w) {
+    return __uint_as_float(__dp4a(w, 1u << (8 * J), 0x4B000000u));
+}
+
+// one pixel: bytes kb, kb+1, kb+2 of the packed words.  Outputs: yS / yH bit patterns (value in
+// byte 1) and the magic-float bits of V (value in byte 0).
+// The two 16-lane halves of a sub-partition must stay balanced: IDP4A/IMAD only run on one half,
+// PRMT/VABSDIFF4 only on the other (everything else uses both).  With the two address IMADs on the
+// first half and 3 packing PRMT + SAD per pixel on the second, lifting TWO of the three bytes with
+// IDP4A and one with PRMT balances them (profiles/r01b_hsv_rate_all_variants.txt).
+#ifndef PSD_V4_PRMT_CHANNELS
+#define PSD_V4_PRMT_CHANNELS 1  // how many of B,G,R are extracted with PRMT instead of IDP4A
+#endif
+template <int KB>
+__device__ __forceinline__ void hsv_px_v4(const uint32_t (&w)[12], const LutView& lut, uint32_t& oh,
+                                          uint32_t& os, uint32_t& ov) {
+    const float B = (PSD_V4_PRMT_CHANNELS >= 3) ? magic_byte<(KB + 0) & 3>(w[(KB + 0) >> 2])
+                                                : magic_byte_dp4a<(KB + 0) & 3>(w[(KB + 0) >> 2]);
+    const float G = (PSD_V4_PRMT_CHANNELS >= 1) ? magic_byte<(KB + 1) & 3>(w[(KB + 1) >> 2])
+                                                : magic_byte_dp4a<(KB + 1) & 3>(w[(KB + 1) >> 2]);
+    const float R = (PSD_V4_PRMT_CHANNELS >= 2) ? magic_byte<(KB + 2) & 3>(w[(KB + 2) >> 2])
+                                                : magic_byte_dp4a<(KB + 2) & 3>(w[(KB + 2) >> 2]);
+    const float V = fmax3(B, G, R);
+    const float mn = fmin3(B, G, R);
+    const float d = V - mn;  // exact, plain float 0..255
+    const uint32_t vbits = __float_as_uint(V);
+    // row address = value * 256: the 0x4B exponent byte of the magic float overflows out of the
+    // 32-bit product, so (2^23 + V) * 256 == V * 256 and (V - mn) * 256 == V*256 - mn*256 (mod 2^32)
+    const uint32_t a_s = vbits * 256u + lut.s_addr;
+    const float sdivp = lds_f32(a_s);
+    const float yS = fma_rz(d, sdivp, 32768.5f);
+    const uint32_t a_h = a_s - __float_as_uint(mn) * 256u;  // one IMAD: (V - mn) * 256 + s_addr
+    const float hdivp = lds_f32(a_h + 128u);                  // hdiv column = sdiv column + 128 B
+    const float hR = G - B;
+    const float hG = fmaf(d, 2.0f, B - R);
+    const float hB = fmaf(d, 4.0f, R - G);
+    const float h = (V == R) ? hR : ((V == G) ? hG : hB);
+    float yH = fma_rm(h, hdivp, 49152.5f);
+    yH = fmaf(fma_sat(yH, -256.0f, 12582912.0f), 180.0f, yH);  // += 180 when the integer part is < 0
+    oh = __float_as_uint(yH);
+    os = __float_as_uint(yS);
+    ov = vbits;
+}
+
+__device__ __forceinline__ void hsv16_v4(const uint32_t (&w)[12], Px16& o, const LutView& lut) {
+    uint32_t h[16], s[16], v[16];
+#define PSD_PX(i) hsv_px_v4<3 * (i)>(w, lut, h[i], s[i], v[i]);
+    PSD_PX(0) PSD_PX(1) PSD_PX(2) PSD_PX(3) PSD_PX(4) PSD_PX(5) PSD_PX(6) PSD_PX(7)
+    PSD_PX(8) PSD_PX(9) PSD_PX(10) PSD_PX(11) PSD_PX(12) PSD_PX(13) PSD_PX(14) PSD_PX(15)
+#undef PSD_PX
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // H, S: byte 1 of each result; V: byte 0
+        o.h[j] = __byte_perm(__byte_perm(h[4 * j], h[4 * j + 1], 0x0051),
+                             __byte_perm(h[4 * j + 2], h[4 * j + 3], 0x0051), 0x5410);
+        o.s[j] = __byte_perm(__byte_perm(s[4 * j], s[4 * j + 1], 0x0051),
+                             __byte_perm(s[4 * j + 2], s[4 * j + 3], 0x0051), 0x5410);
+        o.v[j] = __byte_perm(__byte_perm(v[4 * j], v[4 * j + 1], 0x0040),
+                             __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x0040), 0x5410);
+    }
+}
+
+// fills the replicated LUT (64 KB) - called once per CTA by all threads
+__device__ __forceinline__ void lut_fill(float* lut, int tid, int nthreads) {
+    for (int i = tid; i < 256 * 64; i += nthreads) {
+        const int row = i >> 6, col = i & 63;
+        float v = 0.0f;
+        if (row) {
+            // exact table integers / 4096 (both are exact in float: < 2^21 and a power-of-two divisor)
+            const int sd = __double2int_rn(1044480.0 / (double)row);
+            const int hd = __double2int_rn(737280.0 / (6.0 * (double)row));
+            v = (col < 32) ? (float)sd * 0.000244140625f : (float)hd * 0.000244140625f;
+        }
+        lut[i] = v;
+    }
+}
+
 __device__ __forceinline__ uint32_t y_px(uint32_t b, uint32_t g, uint32_t r) {
     return (r * 4899u + g * 9617u + b * 1868u + 8192u) >> 14;
 }

@@ -56,6 +56,8 @@ struct ScoreArgs {
     int32_t n_chunks;
     int32_t n_strips;
     int32_t tma_ok;          // base pointers and stride 16-byte aligned
+    int32_t px_base;         // first pixel this launch covers (strips are relative to it)
+    int32_t write_has_prev;  // this launch owns the has_prev flags
     psd_frame_sums* sums;    // [n] (pre-zeroed)
     uint32_t* yhist;         // [n][256] (pre-zeroed) or nullptr
     uint32_t* vhist;         // [n][256] (pre-zeroed) or nullptr

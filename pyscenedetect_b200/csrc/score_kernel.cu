@@ -17,15 +17,25 @@
 
 namespace psd {
 
-constexpr int kThreads = 256;
 constexpr int kPxPerThread = 16;
-constexpr int kStripPx = kThreads * kPxPerThread;  // 4096 pixels
-constexpr int kStripBytes = kStripPx * 3;          // 12288 bytes
-constexpr int kStages = 4;
 
+// per-variant launch shape: variant 4 carries a 64 KB replicated LUT, so it runs one large CTA
+// per SM; the table-free variants run three 256-thread CTAs per SM.
+template <int VARIANT>
+struct Shape {
+    static constexpr int kThreads = (VARIANT == 4) ? 768 : 256;
+    static constexpr int kStages = (VARIANT == 4) ? 3 : 4;
+    static constexpr int kMinBlocks = (VARIANT == 4) ? 1 : 3;
+    static constexpr int kLutFloats = (VARIANT == 4) ? 256 * 64 : 4;
+    static constexpr int kStripPx = kThreads * kPxPerThread;
+    static constexpr int kStripBytes = kStripPx * 3;
+};
+
+template <int VARIANT>
 struct __align__(128) ScoreSmem {
-    uint8_t ring[kStages][kStripBytes];
-    unsigned long long full[kStages];
+    uint8_t ring[Shape<VARIANT>::kStages][Shape<VARIANT>::kStripBytes];
+    float lut[Shape<VARIANT>::kLutFloats];
+    unsigned long long full[Shape<VARIANT>::kStages];
     int32_t sdiv[256];
     int32_t hdiv[256];
     uint32_t acc[2][8];        // per-frame CTA partials: sadH, sadS, sadV, bgr (double-buffered)
@@ -33,7 +43,7 @@ struct __align__(128) ScoreSmem {
     uint32_t vhist[2][256];
 };
 
-int score_kernel_smem_bytes() { return (int)sizeof(ScoreSmem); }
+int score_kernel_smem_bytes() { return (int)sizeof(ScoreSmem<2>); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -69,6 +79,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // Cooperative fallback copy for partial strips / unaligned inputs (zero-fills the tail).
+template <int kThreads, int kStripBytes>
 __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int valid_bytes) {
     const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const int full16 = al ? (valid_bytes >> 4) : 0;
@@ -89,9 +100,12 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int 
 }
 
 template <uint32_t F, int VARIANT>
-__global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMinBlocks)
+    psd_score_kernel(const ScoreArgs a) {
+    constexpr int kThreads = Shape<VARIANT>::kThreads, kStages = Shape<VARIANT>::kStages;
+    constexpr int kStripPx = Shape<VARIANT>::kStripPx, kStripBytes = Shape<VARIANT>::kStripBytes;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(smem_raw);
+    ScoreSmem<VARIANT>& sm = *reinterpret_cast<ScoreSmem<VARIANT>*>(smem_raw);
     constexpr bool kHSV = (F & PSD_F_HSV) != 0;
     constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
     constexpr bool kYH = (F & PSD_F_YHIST) != 0;
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
     const int strip = blockIdx.x / a.n_chunks;
     const int f0 = chunk * a.chunk_frames;
     const int nf = min(a.chunk_frames, a.n_frames - f0);
-    const int px0 = strip * kStripPx;
+    const int px0 = a.px_base + strip * kStripPx;
     const int valid_px = min(kStripPx, a.n_pixels - px0);
     const int valid_bytes = valid_px * 3;
     const bool use_tma = a.tma_ok && (valid_px == kStripPx);
@@ -123,6 +137,12 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
         sm.hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
         sm.yhist[0][i] = sm.yhist[1][i] = 0;
         sm.vhist[0][i] = sm.vhist[1][i] = 0;
+    }
+    LutView lut{0u, 0u};
+    if (VARIANT == 4 && kHSV) {
+        lut_fill(sm.lut, tid, kThreads);
+        lut.s_addr = smem_u32(sm.lut) + (tid & 31) * 4;
+        lut.h_addr = lut.s_addr + 128;
     }
     if (tid < 16) sm.acc[tid >> 3][tid & 7] = 0;
     if (tid == 0) {
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
         if (use_tma) {
             mbar_wait(&sm.full[stage], (uint32_t)((k / kStages) & 1));
         } else {
-            coop_copy(sm.ring[stage], frame_ptr(it), valid_bytes);
+            coop_copy<kThreads, kStripBytes>(sm.ring[stage], frame_ptr(it), valid_bytes);
             __syncthreads();
         }
         uint32_t w[12];
@@ -177,12 +197,12 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
                 if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fprev]) + (tid < 3 ? tid : 4),
                                  (unsigned long long)v);
             }
-            if (kYH) {
+            if (kYH && tid < 256) {
                 const uint32_t v = sm.yhist[slot][tid];
                 sm.yhist[slot][tid] = 0;
                 if (v) atomicAdd(&a.yhist[(int64_t)fprev * 256 + tid], v);
             }
-            if (kEDGE) {
+            if (kEDGE && tid < 256) {
                 const uint32_t v = sm.vhist[slot][tid];
                 sm.vhist[slot][tid] = 0;
                 if (v) atomicAdd(&a.vhist[(int64_t)fprev * 256 + tid], v);
@@ -195,7 +215,10 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
         uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
         if (kHSV) {
             Px16 cur;
-            hsv16<VARIANT>(w, cur, sm.sdiv, sm.hdiv);
+            if (VARIANT == 4)
+                hsv16_v4(w, cur, lut);
+            else
+                hsv16<VARIANT>(w, cur, sm.sdiv, sm.hdiv);
             if (prev_valid) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -245,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
                     if (kSUM) atomicAdd(&sm.acc[slot][3], bsum);
                 }
             }
-            if (strip == 0 && tid == 0) a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
+            if (a.write_has_prev && strip == 0 && tid == 0) a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
         }
     }
     __syncthreads();
@@ -257,29 +280,251 @@ __global__ void __launch_bounds__(kThreads, 3) psd_score_kernel(const ScoreArgs 
             if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fprev]) + (tid < 3 ? tid : 4),
                              (unsigned long long)v);
         }
-        if (kYH) {
+        if (kYH && tid < 256) {
             const uint32_t v = sm.yhist[slot][tid];
             if (v) atomicAdd(&a.yhist[(int64_t)fprev * 256 + tid], v);
         }
-        if (kEDGE) {
+        if (kEDGE && tid < 256) {
             const uint32_t v = sm.vhist[slot][tid];
             if (v) atomicAdd(&a.vhist[(int64_t)fprev * 256 + tid], v);
         }
     }
 }
 
-template <uint32_t F, int VARIANT>
-static int launch_one(const ScoreArgs& a, cudaStream_t stream) {
-    static bool configured = false;
-    const int smem = (int)sizeof(ScoreSmem);
-    if (!configured) {
-        PSD_CUDA(cudaFuncSetAttribute(psd_score_kernel<F, VARIANT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised form of the same pass (full, 16-byte aligned strips only).
+// 24 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
+// loop: consumers wait on the stage's FULL mbarrier (TMA complete_tx), pull their 48 bytes, do the
+// arithmetic, add their warp-reduced partials to the stage's shared accumulators and arrive on the
+// stage's EMPTY mbarrier; the producer warp waits for all 24 arrivals, flushes the stage's
+// accumulators / histogram bins to HBM with integer atomics, zeroes them and immediately re-arms
+// the stage with the bulk copy of the frame three iterations ahead.  Warps can therefore drift up
+// to kWsStages frames apart instead of meeting at a __syncthreads every frame.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWsConsumerWarps = 24;
+constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
+constexpr int kWsThreads = kWsConsumers + 32;        // + producer warp
+constexpr int kWsStages = 3;
+constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12288 pixels
+constexpr int kWsStripBytes = kWsStripPx * 3;            // 36864 bytes
+
+struct __align__(128) WsSmem {
+    uint8_t ring[kWsStages][kWsStripBytes];
+    float lut[256 * 64];
+    unsigned long long full[kWsStages];
+    unsigned long long empty[kWsStages];
+    uint32_t acc[kWsStages][8];
+    uint32_t yhist[kWsStages][256];
+    uint32_t vhist[kWsStages][256];
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <uint32_t F>
+__global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const ScoreArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+    constexpr bool kHSV = (F & PSD_F_HSV) != 0;
+    constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
+    constexpr bool kYH = (F & PSD_F_YHIST) != 0;
+    constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int chunk = blockIdx.x % a.n_chunks;
+    const int strip = blockIdx.x / a.n_chunks;
+    const int f0 = chunk * a.chunk_frames;
+    const int nf = min(a.chunk_frames, a.n_frames - f0);
+    const int px0 = strip * kWsStripPx;
+    const bool have_halo = kHSV && (f0 > 0 || a.prev != nullptr);
+    const int it_begin = have_halo ? 0 : 1;
+    const int it_end = nf + 1;
+    const int64_t strip_off = (int64_t)px0 * 3;
+    auto frame_ptr = [&](int it) -> const uint8_t* {
+        const int fi = f0 - 1 + it;
+        return (fi < 0 ? a.prev : a.frames + (int64_t)fi * a.frame_stride) + strip_off;
+    };
+
+    for (int i = tid; i < kWsStages * 256; i += kWsThreads) {
+        (&sm.yhist[0][0])[i] = 0;
+        (&sm.vhist[0][0])[i] = 0;
     }
+    if (tid < kWsStages * 8) (&sm.acc[0][0])[tid] = 0;
+    if (kHSV) lut_fill(sm.lut, tid, kWsThreads);
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kWsConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kWsConsumers) {
+        // ===================== producer warp =====================
+        if (lane == 0) {
+            for (int s = 0; s < kWsStages && it_begin + s < it_end; ++s) {
+                mbar_expect_tx(&sm.full[s], kWsStripBytes);
+                bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), kWsStripBytes, &sm.full[s]);
+            }
+        }
+        for (int it = it_begin; it < it_end; ++it) {
+            const int k = it - it_begin;
+            const int stage = k % kWsStages;
+            mbar_wait(&sm.empty[stage], (uint32_t)((k / kWsStages) & 1));
+            const int fi = f0 - 1 + it;
+            if (it >= 1) {  // this CTA accounts for frame fi (not the halo)
+                if (lane < 4) {
+                    const uint32_t v = sm.acc[stage][lane];
+                    sm.acc[stage][lane] = 0;
+                    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fi]) + (lane < 3 ? lane : 4),
+                                     (unsigned long long)v);
+                }
+                if (kYH) {
+#pragma unroll
+                    for (int b = lane; b < 256; b += 32) {
+                        const uint32_t v = sm.yhist[stage][b];
+                        if (v) { sm.yhist[stage][b] = 0; atomicAdd(&a.yhist[(int64_t)fi * 256 + b], v); }
+                    }
+                }
+                if (kEDGE) {
+#pragma unroll
+                    for (int b = lane; b < 256; b += 32) {
+                        const uint32_t v = sm.vhist[stage][b];
+                        if (v) { sm.vhist[stage][b] = 0; atomicAdd(&a.vhist[(int64_t)fi * 256 + b], v); }
+                    }
+                }
+                if (a.write_has_prev && strip == 0 && lane == 0)
+                    a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
+            }
+            __syncwarp();  // the zeroing above is ordered before lane 0 re-arms the stage
+            if (lane == 0 && it + kWsStages < it_end) {
+                mbar_expect_tx(&sm.full[stage], kWsStripBytes);
+                bulk_g2s(sm.ring[stage], frame_ptr(it + kWsStages), kWsStripBytes, &sm.full[stage]);
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    LutView lut{0u, 0u};
+    lut.s_addr = smem_u32(sm.lut) + lane * 4;
+    lut.h_addr = lut.s_addr + 128;
+    Px16 prev;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
+    bool prev_valid = false;
+    const int my_px = px0 + tid * kPxPerThread;
+
+    for (int it = it_begin; it < it_end; ++it) {
+        const int k = it - it_begin;
+        const int stage = k % kWsStages;
+        mbar_wait(&sm.full[stage], (uint32_t)((k / kWsStages) & 1));
+        uint32_t w[12];
+        {
+            const uint4* p = reinterpret_cast<const uint4*>(sm.ring[stage] + tid * 48);
+            const uint4 q0 = p[0], q1 = p[1], q2 = p[2];
+            w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+            w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+            w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+        }
+        const int fi = f0 - 1 + it;
+        const bool own = (it >= 1);
+        uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
+        if (kHSV) {
+            Px16 cur;
+            hsv16_v4(w, cur, lut);
+            if (prev_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sad_h = __vsadu4(cur.h[j], prev.h[j]) + sad_h;
+                    sad_s = __vsadu4(cur.s[j], prev.s[j]) + sad_s;
+                    sad_v = __vsadu4(cur.v[j], prev.v[j]) + sad_v;
+                }
+            }
+            prev = cur;
+            prev_valid = true;
+            if (kEDGE && own) {
+                uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
+                if ((a.n_pixels & 15) == 0) {
+                    *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
+                } else {
+                    for (int p = 0; p < kPxPerThread; ++p) vp[p] = (uint8_t)(cur.v[p >> 2] >> ((p & 3) * 8));
+                }
+#pragma unroll
+                for (int p = 0; p < kPxPerThread; ++p)
+                    atomicAdd(&sm.vhist[stage][(cur.v[p >> 2] >> ((p & 3) * 8)) & 0xFF], 1u);
+            }
+        }
+        if (own) {
+            if (kSUM) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
+            }
+            if (kYH) {
+#pragma unroll
+                for (int p = 0; p < kPxPerThread; ++p) {
+                    const uint32_t y = y_px(byte_of(w, 3 * p), byte_of(w, 3 * p + 1), byte_of(w, 3 * p + 2));
+                    atomicAdd(&sm.yhist[stage][y], 1u);
+                }
+            }
+            if (kHSV || kSUM) {
+                sad_h = __reduce_add_sync(0xFFFFFFFFu, sad_h);
+                sad_s = __reduce_add_sync(0xFFFFFFFFu, sad_s);
+                sad_v = __reduce_add_sync(0xFFFFFFFFu, sad_v);
+                bsum = __reduce_add_sync(0xFFFFFFFFu, bsum);
+                if (lane == 0) {
+                    if (kHSV) {
+                        atomicAdd(&sm.acc[stage][0], sad_h);
+                        atomicAdd(&sm.acc[stage][1], sad_s);
+                        atomicAdd(&sm.acc[stage][2], sad_v);
+                    }
+                    if (kSUM) atomicAdd(&sm.acc[stage][3], bsum);
+                }
+            }
+        }
+        __syncwarp();  // all lanes' shared atomics / ring reads precede the arrival
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
+}
+
+template <uint32_t F>
+static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
+    const int smem = (int)sizeof(WsSmem);
+    PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    a.n_strips = n_ws_strips;
+    const int64_t grid = (int64_t)a.n_chunks * n_ws_strips;
+    PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
+    psd_score_ws_kernel<F><<<(unsigned)grid, kWsThreads, smem, stream>>>(a);
+    PSD_CHECK_LAUNCH();
+    count_launch();
+    return PSD_OK;
+}
+
+static int dispatch_ws(const ScoreArgs& a, uint32_t f, int n_ws_strips, cudaStream_t s) {
+    switch (f & 15u) {
+#define CASE(F) case F: return launch_ws<F>(a, n_ws_strips, s);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+        CASE(9) CASE(11) CASE(13) CASE(15)
+#undef CASE
+        default:
+            set_error("unsupported feature mask 0x%x", f);
+            return PSD_ERR_INVALID;
+    }
+}
+
+template <uint32_t F, int VARIANT>
+static int launch_one(ScoreArgs a, cudaStream_t stream) {
+    const int smem = (int)sizeof(ScoreSmem<VARIANT>);
+    PSD_CUDA(cudaFuncSetAttribute(psd_score_kernel<F, VARIANT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    a.n_strips = (a.n_pixels - a.px_base + Shape<VARIANT>::kStripPx - 1) / Shape<VARIANT>::kStripPx;
     const int64_t grid = (int64_t)a.n_chunks * a.n_strips;
     PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
-    psd_score_kernel<F, VARIANT><<<(unsigned)grid, kThreads, smem, stream>>>(a);
+    psd_score_kernel<F, VARIANT><<<(unsigned)grid, Shape<VARIANT>::kThreads, smem, stream>>>(a);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;
@@ -302,18 +547,34 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     ScoreArgs a = a_in;
     if (features & PSD_F_EDGES) features |= PSD_F_HSV;
     PSD_REQUIRE(a.n_frames > 0 && a.n_pixels > 0, "empty score launch");
-    a.n_strips = (a.n_pixels + kStripPx - 1) / kStripPx;
     if (a.chunk_frames <= 0) a.chunk_frames = 64;
     a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.frame_stride |
                          reinterpret_cast<uintptr_t>(a.prev);
     a.tma_ok = ((al & 15) == 0) ? 1 : 0;
-    PSD_REQUIRE(variant >= 0 && variant <= 3, "unknown hsv variant %d", variant);
+    a.px_base = 0;
+    a.write_has_prev = 1;
+    if (variant == 5) {
+        // warp-specialised kernel on the full 12288-pixel strips, generic kernel (variant 2) on
+        // the remainder; an unaligned input goes entirely through the generic kernel
+        const int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
+        if (n_ws > 0) {
+            int rc = dispatch_ws(a, features, n_ws, stream);
+            if (rc) return rc;
+            a.px_base = n_ws * kWsStripPx;
+            a.write_has_prev = 0;
+            if (a.px_base >= a.n_pixels) return PSD_OK;
+        }
+        return dispatch<2>(a, features, stream);
+    }
+    // variant 1: scalar integer + MUFU (first correct version), 2: packed f32x2, 4: float LUT
     switch (variant) {
-        case 0: return dispatch<0>(a, features, stream);
         case 1: return dispatch<1>(a, features, stream);
         case 2: return dispatch<2>(a, features, stream);
-        default: return dispatch<3>(a, features, stream);
+        case 4: return dispatch<4>(a, features, stream);
+        default:
+            set_error("hsv variant %d is not built into the score kernel (1, 2, 4, 5 are)", variant);
+            return PSD_ERR_INVALID;
     }
 }
 
@@ -321,10 +582,17 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
 template <int VARIANT>
 __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_t* h, uint8_t* s,
                                     uint8_t* v, uint8_t* y) {
+    extern __shared__ __align__(128) float lutmem[];
     __shared__ int32_t sdiv[256], hdiv[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
+    }
+    LutView lut{0u, 0u};
+    if (VARIANT == 4) {
+        lut_fill(lutmem, threadIdx.x, blockDim.x);
+        lut.s_addr = smem_u32(lutmem) + (threadIdx.x & 31) * 4;
+        lut.h_addr = lut.s_addr + 128;
     }
     __syncthreads();
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
@@ -336,7 +604,10 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
         w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
         Px16 o;
-        hsv16<VARIANT>(w, o, sdiv, hdiv);
+        if (VARIANT == 4)
+            hsv16_v4(w, o, lut);
+        else
+            hsv16<VARIANT>(w, o, sdiv, hdiv);
         *reinterpret_cast<uint4*>(h + g * 16) = make_uint4(o.h[0], o.h[1], o.h[2], o.h[3]);
         *reinterpret_cast<uint4*>(s + g * 16) = make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]);
         *reinterpret_cast<uint4*>(v + g * 16) = make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]);
@@ -345,13 +616,24 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
     }
 }
 
+template <int VARIANT>
+static int run_test_hsv(const uint8_t* d_bgr, int64_t groups, uint8_t* dh, uint8_t* ds, uint8_t* dv,
+                        uint8_t* dy) {
+    const int smem = (VARIANT == 4) ? 65536 : 0;
+    PSD_CUDA(cudaFuncSetAttribute(psd_test_hsv_kernel<VARIANT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    psd_test_hsv_kernel<VARIANT><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy);
+    PSD_CHECK_LAUNCH();
+    return PSD_OK;
+}
+
 }  // namespace psd
 
 extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixels, uint8_t* h_out,
                             uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
     using namespace psd;
     PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
-    PSD_REQUIRE(variant >= 0 && variant <= 3, "unknown hsv variant %d", variant);
+    PSD_REQUIRE(variant >= 0 && variant <= 4, "unknown hsv variant %d", variant);
     PSD_CUDA(cudaSetDevice(device));
     uint8_t *d_bgr = nullptr, *d_out = nullptr;
     PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
@@ -361,15 +643,15 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
     uint8_t* ds = d_out + n_pixels;
     uint8_t* dv = d_out + 2 * n_pixels;
     uint8_t* dy = d_out + 3 * n_pixels;
-    if (variant == 0)
-        psd_test_hsv_kernel<0><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
-    else if (variant == 1)
-        psd_test_hsv_kernel<1><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
-    else if (variant == 2)
-        psd_test_hsv_kernel<2><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
-    else
-        psd_test_hsv_kernel<3><<<1184, 256>>>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
-    PSD_CHECK_LAUNCH();
+    int rc;
+    switch (variant) {
+        case 0: rc = run_test_hsv<0>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 1: rc = run_test_hsv<1>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 2: rc = run_test_hsv<2>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 3: rc = run_test_hsv<3>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        default: rc = run_test_hsv<4>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+    }
+    if (rc) return rc;
     count_launch();
     PSD_CUDA(cudaDeviceSynchronize());
     PSD_CUDA(cudaMemcpy(h_out, dh, (size_t)n_pixels, cudaMemcpyDeviceToHost));

@@ -122,7 +122,7 @@ def test_batched_scene_manager_matches_reference_golden(lib, name, batch):
         _check_stats(case, stats, frames.shape[0])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_hsv_and_y_exhaustive_2_24(lib, variant):
     """Every BGR colour through the device functions of the fused kernel vs cv2."""
     v = np.arange(1 << 24, dtype=np.uint32)
@@ -296,3 +296,36 @@ def test_errors_are_loud(lib):
     eng.close()
     with pytest.raises(ValueError):
         Engine(16, 9, 0)
+
+
+@pytest.mark.parametrize("shape", [(1920, 1080), (640, 360), (3840, 2160), (1000, 37)])
+def test_kernel_variants_agree_at_full_size(lib, shape, monkeypatch):
+    """Every build of the fused pass (scalar, f32x2, LUT, warp-specialised + remainder) produces the
+    same integer sums/histograms on full-size frames; the first frames are also checked against
+    the integer oracle.  (1920x1080 and 3840x2160 exercise the warp-specialised strips.)"""
+    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, DeviceBuffer, Engine, synth_frames_device
+    from pyscenedetect_b200.synth import ScenePlan
+    w, h = shape
+    n = 70 if w * h < 3000000 else 12   # > one 64-frame chunk where memory allows
+    plan = ScenePlan(n, seed=9, min_len=5, max_len=12, noise_shift=29)
+    buf = DeviceBuffer(n * w * h * 3)
+    synth_frames_device(buf.ptr, plan.params, w, h)
+    ref = None
+    for variant in ("5", "4", "2", "1"):
+        monkeypatch.setenv("PSD_HSV_VARIANT", variant)
+        eng = Engine(w, h, F_HSV | F_BGRSUM | F_YHIST, max_batch=128)
+        eng.submit_device(buf.ptr, n)
+        got = (eng.read_sums().tobytes(), eng.read_yhist().tobytes())
+        if ref is None:
+            ref = got
+            first = buf.download(3 * w * h * 3).reshape(3, h, w, 3)
+            sums = eng.read_sums()
+            hsv = [M.bgr_to_hsv(f) for f in first]
+            for i in (1, 2):
+                assert int(sums["sad_hue"][i]) == M.sad(hsv[i][0], hsv[i - 1][0])
+                assert int(sums["sad_sat"][i]) == M.sad(hsv[i][1], hsv[i - 1][1])
+                assert int(sums["sad_lum"][i]) == M.sad(hsv[i][2], hsv[i - 1][2])
+                assert int(sums["bgr_sum"][i]) == int(first[i].astype(np.int64).sum())
+        assert got == ref, f"variant {variant} differs"
+        eng.close()
+    buf.close()

@@ -1,6 +1,6 @@
 // Compute-only rate of the per-pixel HSV + SAD arithmetic (no memory traffic): how many pixels
-// per clock per SM can each formulation in csrc/hsv_math.cuh retire?  The fused kernel needs
-// 2.18 Tpx/s for 100 % of the measured HBM roofline = 7.5 px/clk/SM at 1.965 GHz on 148 SMs.
+// per second can each formulation in csrc/hsv_math.cuh retire?  The fused kernel needs
+// 2.18 Tpx/s for 100 % of the measured HBM roofline (6541.8 GB/s / 3 B per pixel).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hsv_rate hsv_rate.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -10,12 +10,19 @@
 using namespace psd;
 constexpr int ITERS = 2048;
 
-template <int VARIANT>
-__global__ void __launch_bounds__(256, 3) rate_kernel(uint32_t* out, uint32_t seed, long long* cyc) {
+template <int VARIANT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint32_t seed, long long* cyc) {
+    extern __shared__ __align__(128) float lut[];
     __shared__ int32_t sdiv[256], hdiv[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
+    }
+    LutView lv{0, 0};
+    if (VARIANT == 4) {
+        lut_fill(lut, threadIdx.x, blockDim.x);
+        lv.s_addr = (uint32_t)__cvta_generic_to_shared(lut) + (threadIdx.x & 31) * 4;
+        lv.h_addr = lv.s_addr + 128;
     }
     __syncthreads();
     uint32_t w[12];
@@ -29,7 +36,10 @@ __global__ void __launch_bounds__(256, 3) rate_kernel(uint32_t* out, uint32_t se
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
         Px16 cur;
-        hsv16<VARIANT>(w, cur, sdiv, hdiv);
+        if (VARIANT == 4)
+            hsv16_v4(w, cur, lv);
+        else
+            hsv16<VARIANT>(w, cur, sdiv, hdiv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             sh = __vsadu4(cur.h[j], prev.h[j]) + sh;
@@ -45,29 +55,36 @@ __global__ void __launch_bounds__(256, 3) rate_kernel(uint32_t* out, uint32_t se
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int VARIANT>
+template <int VARIANT, int THREADS, int MINB>
 void run(uint32_t* out, long long* cyc) {
-    const int grid = 148 * 3;
-    rate_kernel<VARIANT><<<grid, 256>>>(out, 12345u, cyc);
+    const int grid = 148 * MINB;
+    const int smem = VARIANT == 4 ? 65536 : 0;
+    cudaFuncSetAttribute(rate_kernel<VARIANT, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    rate_kernel<VARIANT, THREADS, MINB><<<grid, THREADS, smem>>>(out, 12345u, cyc);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    rate_kernel<VARIANT><<<grid, 256>>>(out, 12345u, cyc);
+    rate_kernel<VARIANT, THREADS, MINB><<<grid, THREADS, smem>>>(out, 12345u, cyc);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    const double px = (double)grid * 256 * 16 * ITERS;
-    printf("variant %d: %8.3f Gpx/s  (%.3f ms)  = %.2f %% of the 2180 Gpx/s HBM-roofline pixel rate %s\n", VARIANT,
-           px / ms / 1e6, ms, 100.0 * px / ms / 1e6 / 2180.0, err == cudaSuccess ? "" : cudaGetErrorString(err));
+    const double px = (double)grid * THREADS * 16 * ITERS;
+    printf("variant %d (%4d thr x %d CTA/SM): %8.3f Gpx/s  (%.3f ms)  = %.2f %% of the 2180 Gpx/s roofline pixel rate %s\n",
+           VARIANT, THREADS, MINB, px / ms / 1e6, ms, 100.0 * px / ms / 1e6 / 2180.0,
+           err == cudaSuccess ? "" : cudaGetErrorString(err));
 }
 
 int main() {
     uint32_t* out; long long* cyc;
-    cudaMalloc(&out, 148 * 3 * 256 * 4); cudaMalloc(&cyc, 148 * 3 * 8);
-    run<0>(out, cyc);
-    run<1>(out, cyc);
-    run<2>(out, cyc);
-    run<3>(out, cyc);
+    cudaMalloc(&out, 148 * 3 * 1024 * 4); cudaMalloc(&cyc, 148 * 3 * 8);
+    run<0, 256, 3>(out, cyc);
+    run<1, 256, 3>(out, cyc);
+    run<2, 256, 3>(out, cyc);
+    run<3, 256, 3>(out, cyc);
+    run<2, 256, 2>(out, cyc);
+    printf("PSD_V4_PRMT_CHANNELS=%d\n", PSD_V4_PRMT_CHANNELS);
+    run<4, 768, 1>(out, cyc);
+    run<4, 512, 1>(out, cyc);
     return 0;
 }
