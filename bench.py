@@ -391,7 +391,16 @@ def run_ours(args):
         e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
         repeat = (N + ring - 1) // ring
 
-        def e2e_step():
+        def e2e_step_sharded():
+            # N > 1: host frames -> halo over NCCL -> per-rank fused pass -> integer results gathered
+            # on rank 0 -> device scans + cut state machines once (equals the serial run)
+            from pyscenedetect_b200.sharding import TorchComm, detect_sharded
+            comm = TorchComm(device=torch.device("cuda", dev))
+            cuts, _sums = detect_sharded(host_frames, first, total_frames, make_det(), 30.0, comm,
+                                         batch_size=64, n_local=N, pinned=True)
+            return N, (len(cuts) if cuts is not None else 0)
+
+        def e2e_step_single():
             sm = SceneManager(device=dev, batch_size=64)
             sm.auto_downscale = False
             sm.downscale = 1
@@ -399,6 +408,8 @@ def run_ours(args):
             n = sm.detect_scenes(ArrayVideoStream(host_frames, 30.0, pinned=True, repeat=repeat), duration=N)
             cuts = sm.get_cut_list()  # device->host read of the results happens inside detect_scenes
             return n, len(cuts)
+
+        e2e_step = e2e_step_sharded if world > 1 else e2e_step_single
 
         for _ in range(min(args.warmup, 1)):
             e2e_step()
@@ -416,7 +427,8 @@ def run_ours(args):
                 "value": total_frames / float(t[0]), "unit": UNIT,
                 "h2d_bytes_per_step": int(N * fbytes), "d2h_bytes_per_step": int(N * 5 * 8),
                 "steps": e2e_steps, "ms_per_step": 1000.0 * float(t[0]),
-                "api": "SceneManager.detect_scenes(ArrayVideoStream(pinned host frames)) + get_cut_list()",
+                "api": ("SceneManager.detect_scenes(ArrayVideoStream(pinned host frames)) + get_cut_list()"
+                        if world == 1 else "sharding.detect_sharded(pinned host frames, TorchComm(nccl))"),
                 "host_frames": f"{ring} distinct page-locked frames cycled to {N} frames per step",
                 "cuts_found": n_cuts,
             }

@@ -420,18 +420,21 @@ __device__ __forceinline__ void hsv16_v4(const uint32_t (&w)[12], Px16& o, const
     }
 }
 
-// fills the replicated LUT (64 KB) - called once per CTA by all threads
+// fills the replicated LUT (64 KB) - called once per CTA by all threads.  Thread t < 512 computes
+// ONE table value (row t>>1, sdiv or hdiv) and stores its 32 per-lane copies.
 __device__ __forceinline__ void lut_fill(float* lut, int tid, int nthreads) {
-    for (int i = tid; i < 256 * 64; i += nthreads) {
-        const int row = i >> 6, col = i & 63;
+    for (int t = tid; t < 512; t += nthreads) {
+        const int row = t >> 1, which = t & 1;
         float v = 0.0f;
         if (row) {
             // exact table integers / 4096 (both are exact in float: < 2^21 and a power-of-two divisor)
-            const int sd = __double2int_rn(1044480.0 / (double)row);
-            const int hd = __double2int_rn(737280.0 / (6.0 * (double)row));
-            v = (col < 32) ? (float)sd * 0.000244140625f : (float)hd * 0.000244140625f;
+            const int q = which ? __double2int_rn(737280.0 / (6.0 * (double)row))
+                                : __double2int_rn(1044480.0 / (double)row);
+            v = (float)q * 0.000244140625f;
         }
-        lut[i] = v;
+        float4* dst = reinterpret_cast<float4*>(lut + row * 64 + which * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v, v, v, v);
     }
 }
 

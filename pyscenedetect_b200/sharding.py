@@ -142,10 +142,13 @@ class GatheredResults:
 
 
 def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int, detector, fps,
-                   comm, engine_factory=None, results_factory=None, batch_size: int = 64):
+                   comm, engine_factory=None, results_factory=None, batch_size: int = 64,
+                   n_local: int | None = None, pinned: bool = False):
     """Run `detector` over a sequence that is split across ranks by contiguous time range.
 
     frames_local: this rank's frames (n_local,H,W,3) = global frames [first_index, first_index+n_local).
+    If `n_local` is larger than the array, the array is cycled (a page-locked ring of distinct
+    frames, as bench.py's end-to-end leg uses); `pinned=True` DMAs straight from it.
     Returns (cut_frame_numbers, gathered_sums) on rank 0 and (None, None) elsewhere.
     `engine_factory` / `results_factory` exist so the CPU tests can substitute oracle-backed
     scorers; the defaults are the CUDA engine and the C-ABI device scans.
@@ -155,15 +158,20 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
         from .engine import Engine as engine_factory  # noqa: N813
     if results_factory is None:
         results_factory = GatheredResults
-    n_local, h, w = frames_local.shape[0], frames_local.shape[1], frames_local.shape[2]
+    ring, h, w = frames_local.shape[0], frames_local.shape[1], frames_local.shape[2]
+    n_local = ring if n_local is None else int(n_local)
     features = detector.required_features()
     eng = engine_factory(w, h, features, max_batch=batch_size,
                          edge_kernel_size=detector.edge_kernel_size_arg())
-    halo = comm.exchange_halo(frames_local[-1] if n_local else None, (h, w, 3))
+    halo = comm.exchange_halo(frames_local[(n_local - 1) % ring] if n_local else None, (h, w, 3))
     if halo is not None:
         eng.set_halo(halo)
-    for i in range(0, n_local, batch_size):
-        eng.submit(frames_local[i:i + batch_size])
+    i = 0
+    while i < n_local:
+        j = i % ring
+        k = min(batch_size, n_local - i, ring - j)
+        eng.submit(frames_local[j:j + k], pinned=pinned)
+        i += k
     sums = eng.read_sums()
     yh = eng.read_yhist() if features & F_YHIST else None
     counts = [b - a for a, b in zip(shard_bounds(total_frames, comm.world)[:-1],
