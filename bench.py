@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--detector", default="content", choices=["content", "content_edges", "threshold", "histogram"])
+    ap.add_argument("--auto-downscale", action="store_true",
+                    help="score at SceneManager's default auto-downscaled size (256 px wide) instead of full resolution")
     return ap.parse_args()
 
 
@@ -264,7 +266,13 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     max_batch = 2048 if not (features & 8) else 32
-    eng = Engine(W, H, features, device=dev, max_batch=max_batch)
+    sw, sh = W, H
+    if args.auto_downscale:
+        from pyscenedetect_b200.scene_manager import compute_downscale_factor
+        f = compute_downscale_factor(max(W, H))
+        sw, sh = (max(1, round(W / f)), max(1, round(H / f))) if f > 1.0 else (W, H)
+        max_batch = min(max_batch, 1024)
+    eng = Engine(W, H, features, width=sw, height=sh, device=dev, max_batch=max_batch)
     weights = (1.0, 1.0, 1.0, 1.0 if args.detector == "content_edges" else 0.0)
     sums_ptr = None
     n_scan = N
@@ -301,10 +309,10 @@ def run_ours(args):
         sp, hp = eng.device_results()
         st = eng.compute_stream  # scans are ordered after the score kernel on the engine's stream
         if args.detector in ("content", "content_edges"):
-            _capi.check(lib.psd_scan_content(sp, N, W * H, warr, wsum, d_comp.data_ptr(), d_val.data_ptr(), st))
+            _capi.check(lib.psd_scan_content(sp, N, sw * sh, warr, wsum, d_comp.data_ptr(), d_val.data_ptr(), st))
             _capi.check(lib.psd_scan_compare(d_val.data_ptr(), N, 27.0, 0, d_flag.data_ptr(), st))
         elif args.detector == "threshold":
-            _capi.check(lib.psd_scan_average(sp, N, W * H * 3, d_val.data_ptr(), st))
+            _capi.check(lib.psd_scan_average(sp, N, sw * sh * 3, d_val.data_ptr(), st))
         else:
             _capi.check(lib.psd_scan_hist_correl(hp, N, 256, None, d_val.data_ptr(), st))
 
@@ -362,7 +370,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
                 "workload": f"{det_desc} on {N} synthetic {W}x{H} BGR24 frames per GPU "
-                            f"(BASELINE.json configs[1]), seed {args.seed}, full resolution",
+                            f"(BASELINE.json configs[1]), seed {args.seed}, "
+                            + ("full resolution" if (sw, sh) == (W, H) else f"auto-downscaled on the device to {sw}x{sh}"),
                 "frames_per_gpu": N, "total_frames": total_frames,
                 "parallelism": f"{world} contiguous time shards, 1-frame halo over NCCL p2p" if world > 1 else "single GPU",
                 "l2": f"inputs are {N * fbytes / 1e9:.1f} GB per step per GPU, larger than L2 (126 MB): no flush needed",

@@ -157,50 +157,75 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
     }
 }
 
-// ---- 4. dilate (separable max over k) ----
-__global__ void __launch_bounds__(256) psd_dilate_rows_kernel(const uint8_t* __restrict__ map,
-                                                              uint8_t* __restrict__ tmp, int W, int H,
-                                                              int r) {
+// ---- 4. dilate on bit-packed edge maps (32 pixels per word) ----
+// pack: bit i of word (y, wq) = (map[y][32*wq + i] == 2); pixels beyond W are 0
+__global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __restrict__ map,
+                                                            uint32_t* __restrict__ bits, int W, int H,
+                                                            int Wq) {
     const int64_t P = (int64_t)W * H;
-    const int64_t f = blockIdx.y;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const int64_t f = blockIdx.z;
+    const int y = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp -> 32 words of this row
+    const int wq0 = warp * 32;
+    if (wq0 >= Wq) return;
     const uint8_t* row = map + f * P + (int64_t)y * W;
-    uint8_t v = 0;
-    const int xa = max(x - r, 0), xb = min(x + r, W - 1);
-    for (int xx = xa; xx <= xb; ++xx) v |= (row[xx] == 2);
-    tmp[f * P + i] = v;
+    uint32_t mine = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const int x = (wq0 + j) * 32 + lane;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, x < W && row[x] == 2);
+        if (lane == j) mine = b;
+    }
+    if (wq0 + lane < Wq) bits[(f * H + y) * Wq + wq0 + lane] = mine;
 }
 
-__global__ void __launch_bounds__(256) psd_dilate_cols_kernel(const uint8_t* __restrict__ tmp,
-                                                              uint8_t* __restrict__ dil, int W, int H,
-                                                              int r) {
-    const int64_t P = (int64_t)W * H;
+// rows: out = OR over |dx| <= r of the row shifted by dx (funnel shifts across word boundaries)
+__global__ void __launch_bounds__(256) psd_edge_dilate_rows_bits_kernel(const uint32_t* __restrict__ in,
+                                                                        uint32_t* __restrict__ out,
+                                                                        int64_t n_words, int Wq, int r) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const int wq = (int)(i % Wq);
+    const uint32_t cur = in[i];
+    const uint32_t prv = (wq > 0) ? in[i - 1] : 0u;
+    const uint32_t nxt = (wq + 1 < Wq) ? in[i + 1] : 0u;
+    uint32_t o = cur;
+    for (int s = 1; s <= r; ++s) {
+        o |= __funnelshift_r(cur, nxt, s);  // pixel x+s -> bit position of x
+        o |= __funnelshift_l(prv, cur, s);  // pixel x-s
+    }
+    out[i] = o;
+}
+
+// columns + SAD: dil[y] = OR over |dy| <= r of rows[y+dy]; count differing pixels vs previous frame
+__global__ void __launch_bounds__(256) psd_edge_dilate_cols_bits_kernel(const uint32_t* __restrict__ rows,
+                                                                        uint32_t* __restrict__ dil, int H,
+                                                                        int Wq, int r) {
+    const int64_t per_frame = (int64_t)H * Wq;
     const int64_t f = blockIdx.y;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
-    const uint8_t* base = tmp + f * P;
-    uint8_t v = 0;
+    if (i >= per_frame) return;
+    const int y = (int)(i / Wq), wq = (int)(i - (int64_t)y * Wq);
+    const uint32_t* base = rows + f * per_frame + wq;
+    uint32_t o = 0;
     const int ya = max(y - r, 0), yb = min(y + r, H - 1);
-    for (int yy = ya; yy <= yb; ++yy) v |= base[(int64_t)yy * W + x];
-    dil[f * P + i] = v ? 255 : 0;
+    for (int yy = ya; yy <= yb; ++yy) o |= base[(int64_t)yy * Wq];
+    dil[f * per_frame + i] = o;
 }
 
-// ---- 5. SAD of dilated edge maps vs the previous frame ----
-__global__ void __launch_bounds__(256) psd_edge_sad_kernel(const uint8_t* __restrict__ dil,
-                                                           const uint8_t* __restrict__ carry,
-                                                           int64_t P, int have_prev,
-                                                           psd_frame_sums* __restrict__ sums) {
+__global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* __restrict__ dil,
+                                                                const uint32_t* __restrict__ carry,
+                                                                int64_t per_frame, int have_prev,
+                                                                psd_frame_sums* __restrict__ sums) {
     const int64_t f = blockIdx.y;
     if (f == 0 && !have_prev) return;
-    const uint8_t* cur = dil + f * P;
-    const uint8_t* prv = (f == 0) ? carry : dil + (f - 1) * P;
+    const uint32_t* cur = dil + f * per_frame;
+    const uint32_t* prv = (f == 0) ? carry : dil + (f - 1) * per_frame;
     uint32_t cnt = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_frame;
          i += (int64_t)gridDim.x * blockDim.x)
-        cnt += (cur[i] != prv[i]);
+        cnt += __popc(cur[i] ^ prv[i]);
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     __shared__ uint32_t part[8];
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
@@ -210,6 +235,22 @@ __global__ void __launch_bounds__(256) psd_edge_sad_kernel(const uint8_t* __rest
         for (int w = 0; w < 8; ++w) t += part[w];
         if (t) atomicAdd(reinterpret_cast<unsigned long long*>(&sums[f].sad_edges), 255ull * t);
     }
+}
+
+// debug/test tap: bit-packed map -> 0/255 bytes
+__global__ void psd_edge_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __restrict__ out, int W,
+                                       int H, int Wq) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)W * H) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    out[i] = ((bits[(int64_t)y * Wq + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+}
+
+int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, cudaStream_t stream) {
+    const int Wq = (W + 31) / 32;
+    psd_edge_unpack_kernel<<<(unsigned)(((int64_t)W * H + 255) / 256), 256, 0, stream>>>(bits, out, W, H, Wq);
+    PSD_CHECK_LAUNCH();
+    return PSD_OK;
 }
 
 int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have_prev,
@@ -237,17 +278,24 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         if (*b.changed_host == 0) break;
     }
     const int r = ksize / 2;
-    dim3 pg((unsigned)((P + 255) / 256), (unsigned)n);
-    psd_dilate_rows_kernel<<<pg, 256, 0, stream>>>(b.map, b.tmp, W, H, r);
+    const int Wq = (W + 31) / 32;
+    const int64_t per_frame = (int64_t)H * Wq;
+    dim3 kg((unsigned)((Wq + 31) / 32 * 32 + 255) / 256, (unsigned)H, (unsigned)n);  // 8 warps per block
+    kg.x = (unsigned)(((Wq + 31) / 32 + 7) / 8);
+    psd_edge_pack_kernel<<<kg, 256, 0, stream>>>(b.map, b.bits_in, W, H, Wq);
     PSD_CHECK_LAUNCH();
-    psd_dilate_cols_kernel<<<pg, 256, 0, stream>>>(b.tmp, b.dilated, W, H, r);
+    psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
+        b.bits_in, b.bits_row, per_frame * n, Wq, r);
     PSD_CHECK_LAUNCH();
-    dim3 sg((unsigned)min((int64_t)296, (P + 255) / 256), (unsigned)n);
-    psd_edge_sad_kernel<<<sg, 256, 0, stream>>>(b.dilated, b.carry, P, have_prev ? 1 : 0, sums);
+    dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
+    psd_edge_dilate_cols_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_row, b.bits_dil, H, Wq, r);
     PSD_CHECK_LAUNCH();
-    count_launch(3);
-    PSD_CUDA(cudaMemcpyAsync(b.carry, b.dilated + (int64_t)(n - 1) * P, (size_t)P,
-                             cudaMemcpyDeviceToDevice, stream));
+    dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
+    psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
+    PSD_CHECK_LAUNCH();
+    count_launch(4);
+    PSD_CUDA(cudaMemcpyAsync(b.carry_bits, b.bits_dil + (int64_t)(n - 1) * per_frame,
+                             (size_t)per_frame * 4, cudaMemcpyDeviceToDevice, stream));
     return PSD_OK;
 }
 

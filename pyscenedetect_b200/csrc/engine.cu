@@ -249,7 +249,8 @@ void psd_engine_destroy(psd_engine* e) {
     cudaFree(e->small); cudaFree(e->d_xofs); cudaFree(e->d_xa); cudaFree(e->d_yofs); cudaFree(e->d_ya);
     cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.map);
-    cudaFree(e->eb.tmp); cudaFree(e->eb.dilated); cudaFree(e->eb.carry); cudaFree(e->eb.changed);
+    cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
+    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed);
     if (e->eb.changed_host) cudaFreeHost(e->eb.changed_host);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -337,9 +338,12 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         const size_t plane = (size_t)e->P * e->max_batch;
         ENG_CUDA(cudaMalloc(&e->eb.vplane, plane));
         ENG_CUDA(cudaMalloc(&e->eb.map, plane));
-        ENG_CUDA(cudaMalloc(&e->eb.tmp, plane));
-        ENG_CUDA(cudaMalloc(&e->eb.dilated, plane));
-        ENG_CUDA(cudaMalloc(&e->eb.carry, (size_t)e->P));
+        const size_t words = (size_t)e->H * ((e->W + 31) / 32);
+        ENG_CUDA(cudaMalloc(&e->eb.tmp, (size_t)e->P));
+        ENG_CUDA(cudaMalloc(&e->eb.bits_in, words * 4 * e->max_batch));
+        ENG_CUDA(cudaMalloc(&e->eb.bits_row, words * 4 * e->max_batch));
+        ENG_CUDA(cudaMalloc(&e->eb.bits_dil, words * 4 * e->max_batch));
+        ENG_CUDA(cudaMalloc(&e->eb.carry_bits, words * 4));
         ENG_CUDA(cudaMalloc(&e->eb.vhist, (size_t)e->max_batch * 256 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.thresholds, (size_t)e->max_batch * 2 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.changed, 4));
@@ -568,8 +572,16 @@ int psd_engine_debug_plane(psd_engine* e, int which, int64_t index, uint8_t* out
     }
     PSD_REQUIRE(e->features & PSD_F_EDGES, "engine was created without PSD_F_EDGES");
     PSD_REQUIRE(cap >= (size_t)e->P, "buffer too small");
-    const uint8_t* src = which == 1 ? e->eb.vplane : which == 2 ? e->eb.map : which == 3 ? e->eb.dilated : nullptr;
-    PSD_REQUIRE(src, "unknown plane %d", which);
+    PSD_REQUIRE(which >= 1 && which <= 3, "unknown plane %d", which);
+    if (which == 3) {
+        const size_t words = (size_t)e->H * ((e->W + 31) / 32);
+        rc = edge_unpack(e->eb.bits_dil + index * words, e->eb.tmp, e->W, e->H, e->compute_stream);
+        if (rc) return rc;
+        PSD_CUDA(cudaStreamSynchronize(e->compute_stream));
+        PSD_CUDA(cudaMemcpy(out, e->eb.tmp, (size_t)e->P, cudaMemcpyDeviceToHost));
+        return PSD_OK;
+    }
+    const uint8_t* src = which == 1 ? e->eb.vplane : e->eb.map;
     if (which == 2) {
         psd_map_to_255_kernel<<<(unsigned)((e->P + 255) / 256), 256, 0, e->compute_stream>>>(
             src + index * e->P, e->eb.tmp, e->P);

@@ -82,14 +82,17 @@ struct EdgeBuffers {
     uint32_t* vhist;    // [n][256]
     int32_t* thresholds;// [n][2] low, high
     uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis 2 = edge
-    uint8_t* tmp;       // [n][P] row-dilated
-    uint8_t* dilated;   // [n][P] final dilated edges 0/255
-    uint8_t* carry;     // [P] dilated edges of the predecessor frame
+    uint8_t* tmp;       // [P] scratch for debug taps
+    uint32_t* bits_in;  // [n][H][Wq] edge pixels, 32 per word
+    uint32_t* bits_row; // [n][H][Wq] row-dilated
+    uint32_t* bits_dil; // [n][H][Wq] dilated edges
+    uint32_t* carry_bits; // [H][Wq] dilated edges of the predecessor frame
     int32_t* changed;   // device flag
     int32_t* changed_host; // pinned
 };
 int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
                  psd_frame_sums* sums, cudaStream_t stream);
+int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, cudaStream_t stream);
 
 // ---- synthetic generator (synth_kernel.cu) ----
 int launch_synth(uint8_t* out, const int32_t* d_params, int64_t n, int width, int height,

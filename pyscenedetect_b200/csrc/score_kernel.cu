@@ -294,20 +294,22 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised form of the same pass (full, 16-byte aligned strips only).
-// 24 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
+// 25 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
 // loop: consumers wait on the stage's FULL mbarrier (TMA complete_tx), pull their 48 bytes, do the
 // arithmetic, add their warp-reduced partials to the stage's shared accumulators and arrive on the
-// stage's EMPTY mbarrier; the producer warp waits for all 24 arrivals, flushes the stage's
+// stage's EMPTY mbarrier; the producer warp waits for all 25 arrivals, flushes the stage's
 // accumulators / histogram bins to HBM with integer atomics, zeroes them and immediately re-arms
 // the stage with the bulk copy of the frame three iterations ahead.  Warps can therefore drift up
 // to kWsStages frames apart instead of meeting at a __syncthreads every frame.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWsConsumerWarps = 24;
-constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
+// 25 consumer warps: 800 threads x 16 px = 12800-pixel strips, which divide every standard 16:9
+// frame exactly (360p: 18, 720p: 72, 1080p: 162, 4K: 648 strips) - no remainder launch.
+constexpr int kWsConsumerWarps = 25;
+constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 800
 constexpr int kWsThreads = kWsConsumers + 32;        // + producer warp
 constexpr int kWsStages = 3;
-constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12288 pixels
-constexpr int kWsStripBytes = kWsStripPx * 3;            // 36864 bytes
+constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12800 pixels
+constexpr int kWsStripBytes = kWsStripPx * 3;            // 38400 bytes
 
 struct __align__(128) WsSmem {
     uint8_t ring[kWsStages][kWsStripBytes];
@@ -555,7 +557,7 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     a.px_base = 0;
     a.write_has_prev = 1;
     if (variant == 5) {
-        // warp-specialised kernel on the full 12288-pixel strips, generic kernel (variant 2) on
+        // warp-specialised kernel on the full 12800-pixel strips, generic kernel (variant 2) on
         // the remainder; an unaligned input goes entirely through the generic kernel
         const int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
         if (n_ws > 0) {
@@ -564,6 +566,9 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
             a.px_base = n_ws * kWsStripPx;
             a.write_has_prev = 0;
             if (a.px_base >= a.n_pixels) return PSD_OK;
+            // the remainder is a sliver of the frame: shorter time chunks give it enough CTAs
+            a.chunk_frames = 16;
+            a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
         }
         return dispatch<2>(a, features, stream);
     }
