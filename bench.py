@@ -406,7 +406,7 @@ def run_ours(args):
             from pyscenedetect_b200.sharding import TorchComm, detect_sharded
             comm = TorchComm(device=torch.device("cuda", dev))
             cuts, _sums = detect_sharded(host_frames, first, total_frames, make_det(), 30.0, comm,
-                                         batch_size=64, n_local=N, pinned=True)
+                                         batch_size=64, n_local=N, pinned=True, device=dev)
             return N, (len(cuts) if cuts is not None else 0)
 
         def e2e_step_single():

@@ -105,10 +105,14 @@ __global__ void __launch_bounds__(TX* TY) psd_canny_classify_kernel(const uint8_
 // ---- 3. hysteresis: tile-local fix-point, repeated until no tile changes ----
 constexpr int HT = 32;  // tile edge
 
+// Launch i of a round reads flag[i-1] and returns at once when the previous launch changed
+// nothing (the map is at its fix-point), so a round can be enqueued blind without host syncs.
 __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict__ map, int W, int H,
+                                                             const int32_t* __restrict__ prev_changed,
                                                              int32_t* __restrict__ changed) {
     __shared__ uint8_t t[HT + 2][HT + 2 + 2];
     __shared__ int any_weak;
+    if (prev_changed != nullptr && *prev_changed == 0) return;
     const int f = blockIdx.z;
     const int64_t P = (int64_t)W * H;
     uint8_t* m = map + f * P;
@@ -264,16 +268,20 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     PSD_CHECK_LAUNCH();
     count_launch(2);
     dim3 hg((W + HT - 1) / HT, (H + HT - 1) / HT, (unsigned)n);
-    // Each launch reaches a fix-point inside every tile; edges crossing tiles need another round.
+    // Each launch reaches a fix-point inside every tile; edges crossing tiles need another launch.
+    // A round enqueues kRound launches chained through device flags (a launch is a no-op once its
+    // predecessor changed nothing) and only then asks the host whether another round is needed.
+    constexpr int kRound = 8;
     for (int round = 0; round < 100000; ++round) {
-        PSD_CUDA(cudaMemsetAsync(b.changed, 0, sizeof(int32_t), stream));
-        for (int rep = 0; rep < 4; ++rep) {
-            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(b.map, W, H, b.changed);
+        PSD_CUDA(cudaMemsetAsync(b.changed, 0, kRound * sizeof(int32_t), stream));
+        for (int rep = 0; rep < kRound; ++rep) {
+            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(b.map, W, H, rep ? b.changed + rep - 1 : nullptr,
+                                                          b.changed + rep);
             PSD_CHECK_LAUNCH();
         }
-        count_launch(4);
-        PSD_CUDA(cudaMemcpyAsync(b.changed_host, b.changed, sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 stream));
+        count_launch(kRound);
+        PSD_CUDA(cudaMemcpyAsync(b.changed_host, b.changed + kRound - 1, sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, stream));
         PSD_CUDA(cudaStreamSynchronize(stream));
         if (*b.changed_host == 0) break;
     }

@@ -346,7 +346,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         ENG_CUDA(cudaMalloc(&e->eb.carry_bits, words * 4));
         ENG_CUDA(cudaMalloc(&e->eb.vhist, (size_t)e->max_batch * 256 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.thresholds, (size_t)e->max_batch * 2 * 4));
-        ENG_CUDA(cudaMalloc(&e->eb.changed, 4));
+        ENG_CUDA(cudaMalloc(&e->eb.changed, 64));
         ENG_CUDA(cudaHostAlloc((void**)&e->eb.changed_host, 4, cudaHostAllocDefault));
     }
     {

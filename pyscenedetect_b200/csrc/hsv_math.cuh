@@ -442,6 +442,35 @@ __device__ __forceinline__ uint32_t y_px(uint32_t b, uint32_t g, uint32_t r) {
     return (r * 4899u + g * 9617u + b * 1868u + 8192u) >> 14;
 }
 
+// Y of pixel P straight from the packed words with IDP4A: the 14-bit coefficients are split into
+// (lo, hi) bytes, 1868 = 7*256+76, 9617 = 37*256+145, 4899 = 19*256+35, so
+// Y = (dp4a(w, lo) + 256 * dp4a(w, hi) + 8192) >> 14 with per-byte-position coefficient words.
+__host__ __device__ constexpr uint32_t y_coef_word(int word, int k0, int which) {
+    // which: 0 = lo bytes (76,145,35 for B,G,R), 1 = hi bytes (7,37,19)
+    uint32_t r = 0;
+    for (int b = 0; b < 4; ++b) {
+        const int g = 4 * word + b - k0;  // 0,1,2 -> B,G,R of this pixel
+        uint32_t c = 0;
+        if (g == 0) c = which ? 7u : 76u;
+        if (g == 1) c = which ? 37u : 145u;
+        if (g == 2) c = which ? 19u : 35u;
+        r |= c << (8 * b);
+    }
+    return r;
+}
+
+template <int P>
+__device__ __forceinline__ uint32_t y_of_pixel(const uint32_t (&w)[12]) {
+    constexpr int k0 = 3 * P, j0 = k0 >> 2, j1 = (k0 + 2) >> 2;
+    uint32_t lo = __dp4a(w[j0], y_coef_word(j0, k0, 0), 8192u);
+    uint32_t hi = __dp4a(w[j0], y_coef_word(j0, k0, 1), 0u);
+    if (j1 != j0) {
+        lo = __dp4a(w[j1], y_coef_word(j1, k0, 0), lo);
+        hi = __dp4a(w[j1], y_coef_word(j1, k0, 1), hi);
+    }
+    return (hi * 256u + lo) >> 14;
+}
+
 // byte k (0..47) of 12 packed words
 __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[12], int k) {
     return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu;

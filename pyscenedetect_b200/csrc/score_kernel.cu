@@ -294,22 +294,23 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised form of the same pass (full, 16-byte aligned strips only).
-// 25 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
+// 24 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
 // loop: consumers wait on the stage's FULL mbarrier (TMA complete_tx), pull their 48 bytes, do the
 // arithmetic, add their warp-reduced partials to the stage's shared accumulators and arrive on the
-// stage's EMPTY mbarrier; the producer warp waits for all 25 arrivals, flushes the stage's
+// stage's EMPTY mbarrier; the producer warp waits for all 24 arrivals, flushes the stage's
 // accumulators / histogram bins to HBM with integer atomics, zeroes them and immediately re-arms
 // the stage with the bulk copy of the frame three iterations ahead.  Warps can therefore drift up
 // to kWsStages frames apart instead of meeting at a __syncthreads every frame.
 // ---------------------------------------------------------------------------------------------
-// 25 consumer warps: 800 threads x 16 px = 12800-pixel strips, which divide every standard 16:9
-// frame exactly (360p: 18, 720p: 72, 1080p: 162, 4K: 648 strips) - no remainder launch.
-constexpr int kWsConsumerWarps = 25;
-constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 800
+// 24 consumer warps = 6 per sub-partition (25 was measured 4.5 % slower: 7/6/6/6 is unbalanced).
+// A last, partial strip is handled in the same kernel when it is a whole number of 16-pixel
+// thread slices (1080p: 168 full strips + one of 9216 px); other remainders go to the generic kernel.
+constexpr int kWsConsumerWarps = 24;
+constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
 constexpr int kWsThreads = kWsConsumers + 32;        // + producer warp
 constexpr int kWsStages = 3;
-constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12800 pixels
-constexpr int kWsStripBytes = kWsStripPx * 3;            // 38400 bytes
+constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12288 pixels
+constexpr int kWsStripBytes = kWsStripPx * 3;            // 36864 bytes
 
 struct __align__(128) WsSmem {
     uint8_t ring[kWsStages][kWsStripBytes];
@@ -341,6 +342,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     const int f0 = chunk * a.chunk_frames;
     const int nf = min(a.chunk_frames, a.n_frames - f0);
     const int px0 = strip * kWsStripPx;
+    const int valid_px = min(kWsStripPx, a.n_pixels - px0);  // a multiple of 16 (launch_score checks)
+    const uint32_t copy_bytes = (uint32_t)valid_px * 3u;     // hence a multiple of 48
     const bool have_halo = kHSV && (f0 > 0 || a.prev != nullptr);
     const int it_begin = have_halo ? 0 : 1;
     const int it_end = nf + 1;
@@ -369,8 +372,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         // ===================== producer warp =====================
         if (lane == 0) {
             for (int s = 0; s < kWsStages && it_begin + s < it_end; ++s) {
-                mbar_expect_tx(&sm.full[s], kWsStripBytes);
-                bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), kWsStripBytes, &sm.full[s]);
+                mbar_expect_tx(&sm.full[s], copy_bytes);
+                bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), copy_bytes, &sm.full[s]);
             }
         }
         for (int it = it_begin; it < it_end; ++it) {
@@ -404,8 +407,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
             }
             __syncwarp();  // the zeroing above is ordered before lane 0 re-arms the stage
             if (lane == 0 && it + kWsStages < it_end) {
-                mbar_expect_tx(&sm.full[stage], kWsStripBytes);
-                bulk_g2s(sm.ring[stage], frame_ptr(it + kWsStages), kWsStripBytes, &sm.full[stage]);
+                mbar_expect_tx(&sm.full[stage], copy_bytes);
+                bulk_g2s(sm.ring[stage], frame_ptr(it + kWsStages), copy_bytes, &sm.full[stage]);
             }
         }
         return;
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
     bool prev_valid = false;
     const int my_px = px0 + tid * kPxPerThread;
+    const bool active = tid * kPxPerThread < valid_px;  // only the last strip has idle threads
 
     for (int it = it_begin; it < it_end; ++it) {
         const int k = it - it_begin;
@@ -427,8 +431,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         mbar_wait(&sm.full[stage], (uint32_t)((k / kWsStages) & 1));
         uint32_t w[12];
         {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             const uint4* p = reinterpret_cast<const uint4*>(sm.ring[stage] + tid * 48);
-            const uint4 q0 = p[0], q1 = p[1], q2 = p[2];
+            const uint4 q0 = active ? p[0] : z, q1 = active ? p[1] : z, q2 = active ? p[2] : z;
             w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
             w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
             w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
             }
             prev = cur;
             prev_valid = true;
-            if (kEDGE && own) {
+            if (kEDGE && own && active) {
                 uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
                 if ((a.n_pixels & 15) == 0) {
                     *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
@@ -466,12 +471,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
 #pragma unroll
                 for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
             }
-            if (kYH) {
-#pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) {
-                    const uint32_t y = y_px(byte_of(w, 3 * p), byte_of(w, 3 * p + 1), byte_of(w, 3 * p + 2));
-                    atomicAdd(&sm.yhist[stage][y], 1u);
-                }
+            if (kYH && active) {
+                uint32_t* hist = sm.yhist[stage];
+#define PSD_YH(i) atomicAdd(&hist[y_of_pixel<i>(w)], 1u);
+                PSD_YH(0) PSD_YH(1) PSD_YH(2) PSD_YH(3) PSD_YH(4) PSD_YH(5) PSD_YH(6) PSD_YH(7)
+                PSD_YH(8) PSD_YH(9) PSD_YH(10) PSD_YH(11) PSD_YH(12) PSD_YH(13) PSD_YH(14) PSD_YH(15)
+#undef PSD_YH
             }
             if (kHSV || kSUM) {
                 sad_h = __reduce_add_sync(0xFFFFFFFFu, sad_h);
@@ -557,13 +562,19 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     a.px_base = 0;
     a.write_has_prev = 1;
     if (variant == 5) {
-        // warp-specialised kernel on the full 12800-pixel strips, generic kernel (variant 2) on
+        // warp-specialised kernel on the 12288-pixel strips, generic kernel (variant 2) on
         // the remainder; an unaligned input goes entirely through the generic kernel
-        const int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
+        int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
+        int covered = n_ws * kWsStripPx;
+        const int tail = a.n_pixels - covered;
+        if (n_ws > 0 && tail > 0 && (tail % 16) == 0) {  // partial last strip stays in the same kernel
+            n_ws += 1;
+            covered = a.n_pixels;
+        }
         if (n_ws > 0) {
             int rc = dispatch_ws(a, features, n_ws, stream);
             if (rc) return rc;
-            a.px_base = n_ws * kWsStripPx;
+            a.px_base = covered;
             a.write_has_prev = 0;
             if (a.px_base >= a.n_pixels) return PSD_OK;
             // the remainder is a sliver of the frame: shorter time chunks give it enough CTAs

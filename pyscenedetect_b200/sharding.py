@@ -143,7 +143,7 @@ class GatheredResults:
 
 def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int, detector, fps,
                    comm, engine_factory=None, results_factory=None, batch_size: int = 64,
-                   n_local: int | None = None, pinned: bool = False):
+                   n_local: int | None = None, pinned: bool = False, device: int = 0):
     """Run `detector` over a sequence that is split across ranks by contiguous time range.
 
     frames_local: this rank's frames (n_local,H,W,3) = global frames [first_index, first_index+n_local).
@@ -161,7 +161,7 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
     ring, h, w = frames_local.shape[0], frames_local.shape[1], frames_local.shape[2]
     n_local = ring if n_local is None else int(n_local)
     features = detector.required_features()
-    eng = engine_factory(w, h, features, max_batch=batch_size,
+    eng = engine_factory(w, h, features, device=device, max_batch=batch_size,
                          edge_kernel_size=detector.edge_kernel_size_arg())
     halo = comm.exchange_halo(frames_local[(n_local - 1) % ring] if n_local else None, (h, w, 3))
     if halo is not None:
@@ -183,7 +183,7 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
     if comm.rank != 0:
         return None, None
     assert all_sums.dtype == SUMS_DTYPE and all_sums.shape[0] == total_frames
-    res = results_factory(all_sums, all_hist, w * h)
+    res = results_factory(all_sums, all_hist, w * h, device)
     detector.attach_engine(res)
     detector._base_index = 0
     tcs = [FrameTimecode(i, fps) for i in range(total_frames)]
