@@ -329,3 +329,110 @@ def test_kernel_variants_agree_at_full_size(lib, shape, monkeypatch):
         assert got == ref, f"variant {variant} differs"
         eng.close()
     buf.close()
+
+
+def test_full_size_properties_1080p(lib):
+    """Size-independent properties at the benchmark's full frame size (1920x1080), device-resident:
+    identical frames score 0; black<->white gives the extreme sums and the exact correlation
+    -1/(bins-1); contiguous time shards with a halo equal the serial run; re-submitting is
+    idempotent."""
+    from pyscenedetect_b200.engine import F_BGRSUM, F_HSV, F_YHIST, DeviceBuffer, Engine, synth_frames_device
+    from pyscenedetect_b200.synth import ScenePlan
+    w, h = 1920, 1080
+    npx, fb = w * h, w * h * 3
+    feats = F_HSV | F_BGRSUM | F_YHIST
+    # (1)/(2): hand-made frames
+    frames = np.zeros((5, h, w, 3), np.uint8)
+    frames[1] = 255                      # black -> white
+    frames[2] = 255                      # white -> white (identical)
+    frames[3, :, :, 2] = 255             # pure red
+    frames[4, :, :, 2] = 255             # identical again
+    eng = Engine(w, h, feats)
+    eng.submit(frames)
+    s = eng.read_sums()
+    assert (int(s["sad_lum"][1]), int(s["sad_sat"][1]), int(s["sad_hue"][1])) == (255 * npx, 0, 0)
+    assert (int(s["sad_lum"][2]), int(s["sad_sat"][2]), int(s["sad_hue"][2])) == (0, 0, 0)
+    assert (int(s["sad_lum"][3]), int(s["sad_sat"][3]), int(s["sad_hue"][3])) == (0, 255 * npx, 0)
+    assert int(s["sad_lum"][4]) == 0 and int(s["bgr_sum"][4]) == 255 * npx
+    assert int(s["bgr_sum"][1]) == 3 * 255 * npx and int(s["bgr_sum"][0]) == 0
+    val, comps = eng.scan_content((1.0, 1.0, 1.0, 0.0))
+    assert val[1] == 85.0 and val[2] == 0.0 and comps[3][1] == 255.0
+    c = eng.scan_hist_correl(256)
+    assert abs(c[1] - (-1.0 / 255.0)) < 1e-12 and c[2] == 1.0
+    avg = eng.scan_average()
+    assert avg[1] == 255.0 and avg[0] == 0.0 and avg[3] == 85.0
+    eng.close()
+    # (3) shards + halo == serial, (4) idempotence, on a synthetic device-resident sequence
+    n = 96
+    plan = ScenePlan(n, seed=4, min_len=8, max_len=20)
+    buf = DeviceBuffer(n * fb)
+    synth_frames_device(buf.ptr, plan.params, w, h)
+    serial = Engine(w, h, feats, max_batch=128)
+    serial.submit_device(buf.ptr, n)
+    want = (serial.read_sums().tobytes(), serial.read_yhist().tobytes())
+    serial.reset()
+    serial.submit_device(buf.ptr, n)
+    assert (serial.read_sums().tobytes(), serial.read_yhist().tobytes()) == want
+    serial.close()
+    parts_s, parts_h = [], []
+    for a, b in ((0, 31), (31, 64), (64, 96)):
+        e = Engine(w, h, feats, max_batch=16)
+        if a:
+            e.set_halo_device(buf.ptr + (a - 1) * fb)
+        e.submit_device(buf.ptr + a * fb, b - a)
+        parts_s.append(e.read_sums())
+        parts_h.append(e.read_yhist())
+        e.close()
+    assert np.concatenate(parts_s).tobytes() == want[0]
+    assert np.concatenate(parts_h).tobytes() == want[1]
+    buf.close()
+
+
+class _PlainStream:
+    """VideoStream-shaped source WITHOUT read_batch: exercises the pinned double-buffer path."""
+
+    def __init__(self, frames, fps=30.0):
+        from pyscenedetect_b200.video import ArrayVideoStream
+        self._s = ArrayVideoStream(frames, fps)
+
+    frame_size = property(lambda self: self._s.frame_size)
+    frame_rate = property(lambda self: self._s.frame_rate)
+    position = property(lambda self: self._s.position)
+    frame_number = property(lambda self: self._s.frame_number)
+
+    def read(self, decode=True):
+        return self._s.read(decode)
+
+
+def test_scene_manager_plain_stream_crop_and_empty(lib):
+    """Frame-by-frame streams (pinned staging), a crop region (strided view -> packed copy) and an
+    empty stream, against the oracle."""
+    from pyscenedetect_b200 import StatsManager
+    from pyscenedetect_b200.detectors import ContentDetector, ThresholdDetector
+    from pyscenedetect_b200.scene_manager import SceneManager
+    case = get_case("content_default_stats")
+    frames = case_frames(case)
+    stats = StatsManager()
+    sm = SceneManager(stats, batch_size=16)
+    sm.auto_downscale = False
+    sm.add_detector(ContentDetector())
+    sm.add_detector(ThresholdDetector())     # two detectors share one fused pass
+    assert sm.detect_scenes(_PlainStream(frames)) == frames.shape[0]
+    ref = R.RefContentDetector(with_stats=True)
+    want = R.run_detector(ref, frames)
+    rthr = R.RefThresholdDetector()
+    want = sorted(set(want) | set(R.run_detector(rthr, frames)))
+    assert [c.frame_num for c in sm.get_cut_list()] == want
+    # crop
+    sm2 = SceneManager(batch_size=8)
+    sm2.auto_downscale = False
+    sm2.crop = (16, 10, 144, 82)
+    sm2.add_detector(ContentDetector())
+    sm2.detect_scenes(_PlainStream(frames))
+    cropped = np.ascontiguousarray(frames[:, 10:82, 16:144])
+    assert [c.frame_num for c in sm2.get_cut_list()] == R.run_detector(R.RefContentDetector(), cropped)
+    # empty
+    sm3 = SceneManager()
+    sm3.add_detector(ContentDetector())
+    assert sm3.detect_scenes(_PlainStream(frames[:0])) == 0
+    assert sm3.get_cut_list() == [] and sm3.get_scene_list() == []
