@@ -26,7 +26,7 @@ class EngineDetector(SceneDetector):
         self._engine: Engine | None = None
         self._owns_engine = True
         self._device = 0
-        self._max_batch = 64
+        self._max_batch = 16  # strict mode submits one frame per call; staging is sized by this
         self._scored_size: tuple[int, int] | None = None  # (width, height) detectors see
         self._base_index = 0  # engine frame index of this detector's first frame
 

@@ -130,8 +130,8 @@ class SceneManager:
         return sorted(set(self._cutting_list))
 
     def get_scene_list(self, start_in_scene: bool = False) -> list:
-        if self._base_timecode is None:
-            return []
+        if self._base_timecode is None or self._last_pos is None:
+            return []  # nothing processed yet / empty stream
         cut_list = self.get_cut_list()
         scene_list = get_scenes_from_cuts(cut_list, self._start_pos, self._last_pos + 1)
         if not cut_list and not start_in_scene:
