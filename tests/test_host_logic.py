@@ -113,3 +113,21 @@ def test_frame_by_frame_stream_and_crop_and_callback():
     with pytest.raises(TypeError):
         sm.crop = (1.0, 2, 3, 4)
     assert isinstance(np.zeros(1), np.ndarray)
+
+
+def test_plain_stream_crop_empty_host_logic(monkeypatch):
+    """The frame-by-frame (pinned double-buffer) path, crop and the empty stream, with the page-locked
+    buffer replaced by plain numpy memory (no GPU here)."""
+    import numpy as np
+
+    import tests.test_gpu_parity as gpu_tests
+
+    class FakePinned:
+        def __init__(self, nbytes):
+            self.array = np.zeros(nbytes, np.uint8)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(sm_mod, "PinnedBuffer", FakePinned)
+    gpu_tests.test_scene_manager_plain_stream_crop_and_empty(None)
