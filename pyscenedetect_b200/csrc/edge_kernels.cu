@@ -107,17 +107,36 @@ constexpr int HT = 32;  // tile edge
 
 // Launch i of a round reads flag[i-1] and returns at once when the previous launch changed
 // nothing (the map is at its fix-point), so a round can be enqueued blind without host syncs.
+// Per-tile dirty bytes (double-buffered by launch parity) restrict every launch after the first
+// to the frontier: a tile is revisited only if it or one of its 8 neighbours changed last time.
 __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict__ map, int W, int H,
                                                              const int32_t* __restrict__ prev_changed,
-                                                             int32_t* __restrict__ changed) {
+                                                             int32_t* __restrict__ changed,
+                                                             const uint8_t* __restrict__ dirty_prev,
+                                                             uint8_t* __restrict__ dirty_cur) {
     __shared__ uint8_t t[HT + 2][HT + 2 + 2];
     __shared__ int any_weak;
     if (prev_changed != nullptr && *prev_changed == 0) return;
     const int f = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+    const int64_t tile_id = ((int64_t)f * tiles_y + blockIdx.y) * tiles_x + blockIdx.x;
+    if (dirty_prev != nullptr) {
+        bool need = false;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ty = (int)blockIdx.y + dy, tx = (int)blockIdx.x + dx;
+                if (ty >= 0 && ty < tiles_y && tx >= 0 && tx < tiles_x)
+                    need |= dirty_prev[((int64_t)f * tiles_y + ty) * tiles_x + tx] != 0;
+            }
+        if (!need) {
+            if (tid == 0) dirty_cur[tile_id] = 0;
+            return;
+        }
+    }
     const int64_t P = (int64_t)W * H;
     uint8_t* m = map + f * P;
     const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
-    const int tid = threadIdx.x;
     if (tid == 0) any_weak = 0;
     __syncthreads();
     int weak = 0;
@@ -131,7 +150,10 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
     }
     if (weak) any_weak = 1;
     __syncthreads();
-    if (!any_weak) return;
+    if (!any_weak) {
+        if (tid == 0) dirty_cur[tile_id] = 0;
+        return;
+    }
     volatile uint8_t(*vt)[HT + 4] = t;
     int tile_changed = 0;
     while (true) {
@@ -159,6 +181,7 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
         }
         if (tid == 0) atomicExch(changed, 1);
     }
+    if (tid == 0) dirty_cur[tile_id] = tile_changed ? 1 : 0;
 }
 
 // ---- 4. dilate on bit-packed edge maps (32 pixels per word) ----
@@ -272,11 +295,15 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     // A round enqueues kRound launches chained through device flags (a launch is a no-op once its
     // predecessor changed nothing) and only then asks the host whether another round is needed.
     constexpr int kRound = 8;
+    const size_t tiles = (size_t)hg.x * hg.y * n;
     for (int round = 0; round < 100000; ++round) {
         PSD_CUDA(cudaMemsetAsync(b.changed, 0, kRound * sizeof(int32_t), stream));
         for (int rep = 0; rep < kRound; ++rep) {
-            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(b.map, W, H, rep ? b.changed + rep - 1 : nullptr,
-                                                          b.changed + rep);
+            const int launch = round * kRound + rep;
+            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(
+                b.map, W, H, rep ? b.changed + rep - 1 : nullptr, b.changed + rep,
+                launch ? b.dirty + (size_t)((launch - 1) & 1) * tiles : nullptr,
+                b.dirty + (size_t)(launch & 1) * tiles);
             PSD_CHECK_LAUNCH();
         }
         count_launch(kRound);

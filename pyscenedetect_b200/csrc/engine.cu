@@ -250,7 +250,7 @@ void psd_engine_destroy(psd_engine* e) {
     cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.map);
     cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
-    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed);
+    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed); cudaFree(e->eb.dirty);
     if (e->eb.changed_host) cudaFreeHost(e->eb.changed_host);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -347,6 +347,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         ENG_CUDA(cudaMalloc(&e->eb.vhist, (size_t)e->max_batch * 256 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.thresholds, (size_t)e->max_batch * 2 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.changed, 64));
+        ENG_CUDA(cudaMalloc(&e->eb.dirty, (size_t)2 * e->max_batch * ((e->W + 31) / 32) * ((e->H + 31) / 32)));
         ENG_CUDA(cudaHostAlloc((void**)&e->eb.changed_host, 4, cudaHostAllocDefault));
     }
     {

@@ -87,7 +87,8 @@ struct EdgeBuffers {
     uint32_t* bits_row; // [n][H][Wq] row-dilated
     uint32_t* bits_dil; // [n][H][Wq] dilated edges
     uint32_t* carry_bits; // [H][Wq] dilated edges of the predecessor frame
-    int32_t* changed;   // device flag
+    int32_t* changed;   // device flags, one per launch of a hysteresis round
+    uint8_t* dirty;     // [2][n][tiles] per-tile changed bytes (double-buffered)
     int32_t* changed_host; // pinned
 };
 int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
