@@ -39,12 +39,13 @@ __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, i
 }
 
 // ---- 2. Sobel + L1 magnitude + NMS + double threshold ----
-constexpr int TX = 32, TY = 8;
+// 64x16-pixel tiles (4 pixels per thread): the 2-pixel lum halo and 1-pixel gradient halo cost
+// 1.2x / 1.16x redundant work instead of 1.7x / 1.33x with 32x8 tiles, and 4x fewer CTAs.
+constexpr int TX = 64, TY = 16, kClassifyThreads = 256;
 
-__global__ void __launch_bounds__(TX* TY) psd_canny_classify_kernel(const uint8_t* __restrict__ vplane,
-                                                                    const int32_t* __restrict__ thr,
-                                                                    uint8_t* __restrict__ map, int W,
-                                                                    int H) {
+__global__ void __launch_bounds__(kClassifyThreads) psd_canny_classify_kernel(
+    const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint8_t* __restrict__ map, int W,
+    int H) {
     __shared__ uint8_t lum[TY + 4][TX + 4];
     __shared__ int16_t sgx[TY + 2][TX + 2];
     __shared__ int16_t sgy[TY + 2][TX + 2];
@@ -52,14 +53,14 @@ __global__ void __launch_bounds__(TX* TY) psd_canny_classify_kernel(const uint8_
     const int64_t P = (int64_t)W * H;
     const uint8_t* src = vplane + f * P;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int tid = threadIdx.y * TX + threadIdx.x;
-    for (int i = tid; i < (TY + 4) * (TX + 4); i += TX * TY) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (TY + 4) * (TX + 4); i += kClassifyThreads) {
         const int ly = i / (TX + 4), lx = i - ly * (TX + 4);
         const int gy = min(max(y0 + ly - 2, 0), H - 1), gx = min(max(x0 + lx - 2, 0), W - 1);  // replicate
         lum[ly][lx] = src[(int64_t)gy * W + gx];
     }
     __syncthreads();
-    for (int i = tid; i < (TY + 2) * (TX + 2); i += TX * TY) {
+    for (int i = tid; i < (TY + 2) * (TX + 2); i += kClassifyThreads) {
         const int ly = i / (TX + 2), lx = i - ly * (TX + 2);
         const int gy = y0 + ly - 1, gx = x0 + lx - 1;
         int dx = 0, dy = 0;
@@ -75,35 +76,38 @@ __global__ void __launch_bounds__(TX* TY) psd_canny_classify_kernel(const uint8_
         sgy[ly][lx] = (int16_t)dy;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int ly = threadIdx.y + 1, lx = threadIdx.x + 1;
-    auto mag = [&](int yy, int xx) { return abs((int)sgx[yy][xx]) + abs((int)sgy[yy][xx]); };
-    const int gx = sgx[ly][lx], gy = sgy[ly][lx];
-    const int m = abs(gx) + abs(gy);
     const int low = thr[2 * f], high = thr[2 * f + 1];
-    uint8_t out = 0;
-    if (m > low) {
-        const int ax = abs(gx);
-        const int ay = abs(gy) << 15;
-        const int tg22x = ax * 13573;
-        const int tg67x = tg22x + (ax << 16);
-        bool keep;
-        if (ay < tg22x) {
-            keep = (m > mag(ly, lx - 1)) && (m >= mag(ly, lx + 1));
-        } else if (ay > tg67x) {
-            keep = (m > mag(ly - 1, lx)) && (m >= mag(ly + 1, lx));
-        } else {
-            const int s = ((gx ^ gy) < 0) ? -1 : 1;
-            keep = (m > mag(ly - 1, lx - s)) && (m > mag(ly + 1, lx + s));
+    auto mag = [&](int yy, int xx) { return abs((int)sgx[yy][xx]) + abs((int)sgy[yy][xx]); };
+    for (int i = tid; i < TX * TY; i += kClassifyThreads) {
+        const int ty = i / TX, tx = i - ty * TX;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= W || y >= H) continue;
+        const int ly = ty + 1, lx = tx + 1;
+        const int gx = sgx[ly][lx], gy = sgy[ly][lx];
+        const int m = abs(gx) + abs(gy);
+        uint8_t out = 0;
+        if (m > low) {
+            const int ax = abs(gx);
+            const int ay = abs(gy) << 15;
+            const int tg22x = ax * 13573;
+            const int tg67x = tg22x + (ax << 16);
+            bool keep;
+            if (ay < tg22x) {
+                keep = (m > mag(ly, lx - 1)) && (m >= mag(ly, lx + 1));
+            } else if (ay > tg67x) {
+                keep = (m > mag(ly - 1, lx)) && (m >= mag(ly + 1, lx));
+            } else {
+                const int s = ((gx ^ gy) < 0) ? -1 : 1;
+                keep = (m > mag(ly - 1, lx - s)) && (m > mag(ly + 1, lx + s));
+            }
+            if (keep) out = (m > high) ? 2 : 1;
         }
-        if (keep) out = (m > high) ? 2 : 1;
+        map[f * P + (int64_t)y * W + x] = out;
     }
-    map[f * P + (int64_t)y * W + x] = out;
 }
 
 // ---- 3. hysteresis: tile-local fix-point, repeated until no tile changes ----
-constexpr int HT = 32;  // tile edge
+constexpr int HTX = 64, HTY = 32;  // tile size (pixels)
 
 // Launch i of a round reads flag[i-1] and returns at once when the previous launch changed
 // nothing (the map is at its fix-point), so a round can be enqueued blind without host syncs.
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
                                                              int32_t* __restrict__ changed,
                                                              const uint8_t* __restrict__ dirty_prev,
                                                              uint8_t* __restrict__ dirty_cur) {
-    __shared__ uint8_t t[HT + 2][HT + 2 + 2];
+    __shared__ uint8_t t[HTY + 2][HTX + 2 + 2];
     __shared__ int any_weak;
     if (prev_changed != nullptr && *prev_changed == 0) return;
     const int f = blockIdx.z;
@@ -136,17 +140,17 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
     }
     const int64_t P = (int64_t)W * H;
     uint8_t* m = map + f * P;
-    const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+    const int x0 = blockIdx.x * HTX, y0 = blockIdx.y * HTY;
     if (tid == 0) any_weak = 0;
     __syncthreads();
     int weak = 0;
-    for (int i = tid; i < (HT + 2) * (HT + 2); i += 256) {
-        const int ly = i / (HT + 2), lx = i - ly * (HT + 2);
+    for (int i = tid; i < (HTY + 2) * (HTX + 2); i += 256) {
+        const int ly = i / (HTX + 2), lx = i - ly * (HTX + 2);
         const int gy = y0 + ly - 1, gx = x0 + lx - 1;
         uint8_t v = 0;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = m[(int64_t)gy * W + gx];
         t[ly][lx] = v;
-        if (v == 1 && ly >= 1 && ly <= HT && lx >= 1 && lx <= HT) weak = 1;
+        if (v == 1 && ly >= 1 && ly <= HTY && lx >= 1 && lx <= HTX) weak = 1;
     }
     if (weak) any_weak = 1;
     __syncthreads();
@@ -154,12 +158,12 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
         if (tid == 0) dirty_cur[tile_id] = 0;
         return;
     }
-    volatile uint8_t(*vt)[HT + 4] = t;
+    volatile uint8_t(*vt)[HTX + 4] = t;
     int tile_changed = 0;
     while (true) {
         int ch = 0;
-        for (int i = tid; i < HT * HT; i += 256) {
-            const int ly = 1 + i / HT, lx = 1 + (i % HT);
+        for (int i = tid; i < HTX * HTY; i += 256) {
+            const int ly = 1 + i / HTX, lx = 1 + (i % HTX);
             if (vt[ly][lx] == 1) {
                 const bool s = vt[ly - 1][lx - 1] == 2 || vt[ly - 1][lx] == 2 || vt[ly - 1][lx + 1] == 2 ||
                                vt[ly][lx - 1] == 2 || vt[ly][lx + 1] == 2 || vt[ly + 1][lx - 1] == 2 ||
@@ -174,8 +178,8 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
         tile_changed = 1;
     }
     if (tile_changed) {
-        for (int i = tid; i < HT * HT; i += 256) {
-            const int ly = 1 + i / HT, lx = 1 + (i % HT);
+        for (int i = tid; i < HTX * HTY; i += 256) {
+            const int ly = 1 + i / HTX, lx = 1 + (i % HTX);
             const int gy = y0 + ly - 1, gx = x0 + lx - 1;
             if (gy < H && gx < W && t[ly][lx] == 2) m[(int64_t)gy * W + gx] = 2;
         }
@@ -287,10 +291,10 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     psd_edge_thresholds_kernel<<<(n + 63) / 64, 64, 0, stream>>>(b.vhist, n, P, b.thresholds);
     PSD_CHECK_LAUNCH();
     dim3 cg((W + TX - 1) / TX, (H + TY - 1) / TY, (unsigned)n);
-    psd_canny_classify_kernel<<<cg, dim3(TX, TY), 0, stream>>>(b.vplane, b.thresholds, b.map, W, H);
+    psd_canny_classify_kernel<<<cg, kClassifyThreads, 0, stream>>>(b.vplane, b.thresholds, b.map, W, H);
     PSD_CHECK_LAUNCH();
     count_launch(2);
-    dim3 hg((W + HT - 1) / HT, (H + HT - 1) / HT, (unsigned)n);
+    dim3 hg((W + HTX - 1) / HTX, (H + HTY - 1) / HTY, (unsigned)n);
     // Each launch reaches a fix-point inside every tile; edges crossing tiles need another launch.
     // A round enqueues kRound launches chained through device flags (a launch is a no-op once its
     // predecessor changed nothing) and only then asks the host whether another round is needed.

@@ -153,7 +153,7 @@ static int run_batch(psd_engine* e, const uint8_t* src, int64_t src_frame_stride
     a.frame_stride = scored_stride;
     a.n_frames = (int32_t)n;
     a.n_pixels = (int32_t)e->P;
-    a.chunk_frames = 64;
+    a.chunk_frames = 0;  // launch_score picks the time-chunk length
     a.sums = e->d_sums + slot0;
     a.yhist = (e->features & PSD_F_YHIST) ? e->d_yhist + slot0 * 256 : nullptr;
     a.vhist = (e->features & PSD_F_EDGES) ? e->eb.vhist : nullptr;

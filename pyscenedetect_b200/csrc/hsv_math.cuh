@@ -420,6 +420,66 @@ __device__ __forceinline__ void hsv16_v4(const uint32_t (&w)[12], Px16& o, const
     }
 }
 
+// ---- variant 4 on pixel PAIRS: same arithmetic, but the float adds/FMAs of two pixels share one
+// FADD2/FFMA2 issue slot (the kernel is issue-bound, the FMA pipe has slack). ----
+template <int KB>
+__device__ __forceinline__ void hsv_pair_v4(const uint32_t (&w)[12], const LutView& lut, uint32_t (&oh)[2],
+                                            uint32_t (&os)[2], uint32_t (&ov)[2]) {
+    constexpr int K0 = KB, K1 = KB + 3;
+    const float B0 = magic_byte_dp4a<(K0 + 0) & 3>(w[(K0 + 0) >> 2]);
+    const float G0 = magic_byte<(K0 + 1) & 3>(w[(K0 + 1) >> 2]);
+    const float R0 = magic_byte_dp4a<(K0 + 2) & 3>(w[(K0 + 2) >> 2]);
+    const float B1 = magic_byte_dp4a<(K1 + 0) & 3>(w[(K1 + 0) >> 2]);
+    const float G1 = magic_byte<(K1 + 1) & 3>(w[(K1 + 1) >> 2]);
+    const float R1 = magic_byte_dp4a<(K1 + 2) & 3>(w[(K1 + 2) >> 2]);
+    const float V0 = fmax3(B0, G0, R0), V1 = fmax3(B1, G1, R1);
+    const float m0 = fmin3(B0, G0, R0), m1 = fmin3(B1, G1, R1);
+    const f32x2_t B2 = pack2(B0, B1), G2 = pack2(G0, G1), R2 = pack2(R0, R1);
+    const f32x2_t d2 = sub2(pack2(V0, V1), pack2(m0, m1));
+    const uint32_t as0 = __float_as_uint(V0) * 256u + lut.s_addr;
+    const uint32_t as1 = __float_as_uint(V1) * 256u + lut.s_addr;
+    const f32x2_t sdivp = pack2(lds_f32(as0), lds_f32(as1));
+    const f32x2_t hdivp = pack2(lds_f32(as0 - __float_as_uint(m0) * 256u + 128u),
+                                lds_f32(as1 - __float_as_uint(m1) * 256u + 128u));
+    const f32x2_t yS = fma2_rz(d2, sdivp, pack2(32768.5f, 32768.5f));
+    const f32x2_t hR = sub2(G2, B2);
+    const f32x2_t hG = fma2_rn(d2, pack2(2.0f, 2.0f), sub2(B2, R2));
+    const f32x2_t hB = fma2_rn(d2, pack2(4.0f, 4.0f), sub2(R2, G2));
+    float hR0, hR1, hG0, hG1, hB0, hB1;
+    unpack2(hR, hR0, hR1);
+    unpack2(hG, hG0, hG1);
+    unpack2(hB, hB0, hB1);
+    const float h0 = (V0 == R0) ? hR0 : ((V0 == G0) ? hG0 : hB0);
+    const float h1 = (V1 == R1) ? hR1 : ((V1 == G1) ? hG1 : hB1);
+    float yH0, yH1;
+    unpack2(fma2_rm(pack2(h0, h1), hdivp, pack2(49152.5f, 49152.5f)), yH0, yH1);
+    const f32x2_t mfix = pack2(fma_sat(yH0, -256.0f, 12582912.0f), fma_sat(yH1, -256.0f, 12582912.0f));
+    unpack2(fma2_rn(mfix, pack2(180.0f, 180.0f), pack2(yH0, yH1)), yH0, yH1);
+    float yS0, yS1;
+    unpack2(yS, yS0, yS1);
+    oh[0] = __float_as_uint(yH0); oh[1] = __float_as_uint(yH1);
+    os[0] = __float_as_uint(yS0); os[1] = __float_as_uint(yS1);
+    ov[0] = __float_as_uint(V0); ov[1] = __float_as_uint(V1);
+}
+
+__device__ __forceinline__ void hsv16_v4pair(const uint32_t (&w)[12], Px16& o, const LutView& lut) {
+    uint32_t h[16], s[16], v[16];
+#define PSD_PAIR(i) { uint32_t a[2], b[2], c[2]; hsv_pair_v4<6 * (i)>(w, lut, a, b, c); \
+        h[2 * (i)] = a[0]; h[2 * (i) + 1] = a[1]; s[2 * (i)] = b[0]; s[2 * (i) + 1] = b[1]; \
+        v[2 * (i)] = c[0]; v[2 * (i) + 1] = c[1]; }
+    PSD_PAIR(0) PSD_PAIR(1) PSD_PAIR(2) PSD_PAIR(3) PSD_PAIR(4) PSD_PAIR(5) PSD_PAIR(6) PSD_PAIR(7)
+#undef PSD_PAIR
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o.h[j] = __byte_perm(__byte_perm(h[4 * j], h[4 * j + 1], 0x0051),
+                             __byte_perm(h[4 * j + 2], h[4 * j + 3], 0x0051), 0x5410);
+        o.s[j] = __byte_perm(__byte_perm(s[4 * j], s[4 * j + 1], 0x0051),
+                             __byte_perm(s[4 * j + 2], s[4 * j + 3], 0x0051), 0x5410);
+        o.v[j] = __byte_perm(__byte_perm(v[4 * j], v[4 * j + 1], 0x0040),
+                             __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x0040), 0x5410);
+    }
+}
+
 // fills the replicated LUT (64 KB) - called once per CTA by all threads.  Thread t < 512 computes
 // ONE table value (row t>>1, sdiv or hdiv) and stores its 32 per-lane copies.
 __device__ __forceinline__ void lut_fill(float* lut, int tid, int nthreads) {

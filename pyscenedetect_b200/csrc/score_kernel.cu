@@ -443,7 +443,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
         if (kHSV) {
             Px16 cur;
+#ifdef PSD_WS_PAIR_V4
+            hsv16_v4pair(w, cur, lut);  // FADD2/FFMA2 on pixel pairs: 12 % fewer issue slots, but measured
+                                        // 1 % slower in the kernel and 5 % slower compute-only (pipe-bound)
+#else
             hsv16_v4(w, cur, lut);
+#endif
             if (prev_valid) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -554,7 +559,13 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     ScoreArgs a = a_in;
     if (features & PSD_F_EDGES) features |= PSD_F_HSV;
     PSD_REQUIRE(a.n_frames > 0 && a.n_pixels > 0, "empty score launch");
-    if (a.chunk_frames <= 0) a.chunk_frames = 64;
+    if (a.chunk_frames <= 0) {
+        // Longer time chunks amortise the per-CTA prologue (LUT fill, first TMA) and the recomputed
+        // halo frame (1/chunk); keep at least ~16 waves of CTAs on the 148 SMs.
+        const int64_t strips = (a.n_pixels + kWsStripPx - 1) / kWsStripPx;
+        a.chunk_frames = (strips * (a.n_frames / 128) >= 148 * 16) ? 128 : 64;
+        if (const char* c = getenv("PSD_CHUNK_FRAMES")) a.chunk_frames = atoi(c) > 0 ? atoi(c) : a.chunk_frames;
+    }
     a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.frame_stride |
                          reinterpret_cast<uintptr_t>(a.prev);
@@ -605,7 +616,7 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
     }
     LutView lut{0u, 0u};
-    if (VARIANT == 4) {
+    if (VARIANT == 4 || VARIANT == 6) {
         lut_fill(lutmem, threadIdx.x, blockDim.x);
         lut.s_addr = smem_u32(lutmem) + (threadIdx.x & 31) * 4;
         lut.h_addr = lut.s_addr + 128;
@@ -620,7 +631,9 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
         w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
         Px16 o;
-        if (VARIANT == 4)
+        if (VARIANT == 6)
+            hsv16_v4pair(w, o, lut);
+        else if (VARIANT == 4)
             hsv16_v4(w, o, lut);
         else
             hsv16<VARIANT>(w, o, sdiv, hdiv);
@@ -635,7 +648,7 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
 template <int VARIANT>
 static int run_test_hsv(const uint8_t* d_bgr, int64_t groups, uint8_t* dh, uint8_t* ds, uint8_t* dv,
                         uint8_t* dy) {
-    const int smem = (VARIANT == 4) ? 65536 : 0;
+    const int smem = (VARIANT == 4 || VARIANT == 6) ? 65536 : 0;
     PSD_CUDA(cudaFuncSetAttribute(psd_test_hsv_kernel<VARIANT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     psd_test_hsv_kernel<VARIANT><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy);
@@ -649,7 +662,7 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
                             uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
     using namespace psd;
     PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
-    PSD_REQUIRE(variant >= 0 && variant <= 4, "unknown hsv variant %d", variant);
+    PSD_REQUIRE((variant >= 0 && variant <= 4) || variant == 6, "unknown hsv variant %d", variant);
     PSD_CUDA(cudaSetDevice(device));
     uint8_t *d_bgr = nullptr, *d_out = nullptr;
     PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
@@ -665,7 +678,8 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
         case 1: rc = run_test_hsv<1>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
         case 2: rc = run_test_hsv<2>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
         case 3: rc = run_test_hsv<3>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        default: rc = run_test_hsv<4>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 4: rc = run_test_hsv<4>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        default: rc = run_test_hsv<6>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
     }
     if (rc) return rc;
     count_launch();

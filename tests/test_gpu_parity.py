@@ -122,7 +122,7 @@ def test_batched_scene_manager_matches_reference_golden(lib, name, batch):
         _check_stats(case, stats, frames.shape[0])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 def test_hsv_and_y_exhaustive_2_24(lib, variant):
     """Every BGR colour through the device functions of the fused kernel vs cv2."""
     v = np.arange(1 << 24, dtype=np.uint32)

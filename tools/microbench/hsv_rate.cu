@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
     }
     LutView lv{0, 0};
-    if (VARIANT == 4) {
+    if (VARIANT == 4 || VARIANT == 6) {
         lut_fill(lut, threadIdx.x, blockDim.x);
         lv.s_addr = (uint32_t)__cvta_generic_to_shared(lut) + (threadIdx.x & 31) * 4;
         lv.h_addr = lv.s_addr + 128;
@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
         Px16 cur;
-        if (VARIANT == 4)
+        if (VARIANT == 6)
+            hsv16_v4pair(w, cur, lv);
+        else if (VARIANT == 4)
             hsv16_v4(w, cur, lv);
         else
             hsv16<VARIANT>(w, cur, sdiv, hdiv);
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
 template <int VARIANT, int THREADS, int MINB>
 void run(uint32_t* out, long long* cyc) {
     const int grid = 148 * MINB;
-    const int smem = VARIANT == 4 ? 65536 : 0;
+    const int smem = (VARIANT == 4 || VARIANT == 6) ? 65536 : 0;
     cudaFuncSetAttribute(rate_kernel<VARIANT, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     rate_kernel<VARIANT, THREADS, MINB><<<grid, THREADS, smem>>>(out, 12345u, cyc);
     cudaDeviceSynchronize();
@@ -85,6 +87,6 @@ int main() {
     run<2, 256, 2>(out, cyc);
     printf("PSD_V4_PRMT_CHANNELS=%d\n", PSD_V4_PRMT_CHANNELS);
     run<4, 768, 1>(out, cyc);
-    run<4, 512, 1>(out, cyc);
+    run<6, 768, 1>(out, cyc);
     return 0;
 }

@@ -43,6 +43,9 @@ DEF_KERNEL(k_ffma, F32DECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c
 DEF_KERNEL(k_ffma_rz, F32DECL, asm volatile("fma.rz.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)))
 DEF_KERNEL(k_fadd, F32DECL, asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[c]) : "f"(a)))
 DEF_KERNEL(k_fmnmx, F32DECL, asm volatile("max.f32 %0, %0, %1;" : "+f"(f[c]) : "f"(a)))
+DEF_KERNEL(k_fmnmx3, F32DECL, asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)))
+DEF_KERNEL(k_fsetp_fsel, F32DECL, { float t; asm volatile("{ .reg .pred p; setp.lt.f32 p, %1, %2; selp.f32 %0, %1, %3, p; }" : "=f"(t) : "f"(f[c]), "f"(a), "f"(b)); f[c] = t + a; })
+DEF_KERNEL(k_ffma_sat, F32DECL, asm volatile("fma.rn.sat.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)))
 DEF_KERNEL(k_mufu_rcp, F32DECL, asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[c])))
 DEF_KERNEL(k_i2fp, F32DECL, f[c] = __int2float_rn(__float_as_int(f[c]) & 0xFF) + a)
 DEF_KERNEL(k_fsetp_sel, F32DECL, f[c] = (f[c] < a) ? f[c] + b : f[c])
@@ -59,6 +62,11 @@ DEF_KERNEL(k_fadd2, F2DECL, asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[c])
 DEF_KERNEL(k_mix_ffma_iadd, MIXDECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(y)))
 DEF_KERNEL(k_mix_ffma_prmt, MIXDECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("prmt.b32 %0, %0, %1, 0x4321;" : "+r"(x[c]) : "r"(y)))
 DEF_KERNEL(k_mix_imad_lop3, MIXDECL, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); f[c] = __uint_as_float(__float_as_uint(f[c]) ^ y))
+DEF_KERNEL(k_mix_idp_prmt, MIXDECL, x[c] = __dp4a(x[c], y, z); f[c] = __uint_as_float(__byte_perm(__float_as_uint(f[c]), y, 0x4321)))
+DEF_KERNEL(k_mix_fmnmx3_prmt, MIXDECL, asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("prmt.b32 %0, %0, %1, 0x4321;" : "+r"(x[c]) : "r"(y)))
+DEF_KERNEL(k_mix_fmnmx3_imad, MIXDECL, asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)))
+DEF_KERNEL(k_mix_ffma_imad, MIXDECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)))
+DEF_KERNEL(k_mix_ffma2_prmt_imad, MIXDECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); z = __byte_perm(z, y, 0x4321))
 DEF_KERNEL(k_mix_ffma_mufu, MIXDECL, asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(a), "f"(b)); if (c < 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[c])); x[c] += y)
 #undef SINK
 // shared-memory lookups: conflict-free per-lane replicated table vs plain 256-entry table
@@ -93,7 +101,7 @@ static void run(const char* name, K kernel, int ops_per_body, uint32_t* out, lon
 int main() {
     uint32_t* out; long long* cyc;
     cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
-    for (int threads : {1024, 512}) {
+    for (int threads : {1024}) {
         run("IADD", k_iadd3, 1, out, cyc, threads);
         run("LOP3", k_lop3, 1, out, cyc, threads);
         run("PRMT", k_prmt, 1, out, cyc, threads);
@@ -109,6 +117,9 @@ int main() {
         run("FFMA.RZ", k_ffma_rz, 1, out, cyc, threads);
         run("FADD", k_fadd, 1, out, cyc, threads);
         run("FMNMX", k_fmnmx, 1, out, cyc, threads);
+        run("FMNMX3", k_fmnmx3, 1, out, cyc, threads);
+        run("FSETP+FSEL+FADD", k_fsetp_fsel, 3, out, cyc, threads);
+        run("FFMA.SAT", k_ffma_sat, 1, out, cyc, threads);
         run("MUFU.RCP", k_mufu_rcp, 1, out, cyc, threads);
         run("LOP+I2FP+FADD", k_i2fp, 3, out, cyc, threads);
         run("FSETP+FADD+SEL", k_fsetp_sel, 3, out, cyc, threads);
@@ -118,6 +129,11 @@ int main() {
         run("mix FFMA+IADD", k_mix_ffma_iadd, 2, out, cyc, threads);
         run("mix FFMA+PRMT", k_mix_ffma_prmt, 2, out, cyc, threads);
         run("mix IMAD+LOP3", k_mix_imad_lop3, 2, out, cyc, threads);
+        run("mix IDP4A+PRMT", k_mix_idp_prmt, 2, out, cyc, threads);
+        run("mix FMNMX3+PRMT", k_mix_fmnmx3_prmt, 2, out, cyc, threads);
+        run("mix FMNMX3+IMAD", k_mix_fmnmx3_imad, 2, out, cyc, threads);
+        run("mix FFMA+IMAD", k_mix_ffma_imad, 2, out, cyc, threads);
+        run("mix FFMA+IMAD+PRMT", k_mix_ffma2_prmt_imad, 3, out, cyc, threads);
         run("mix 8FFMA+2MUFU+8IADD", k_mix_ffma_mufu, 2, out, cyc, threads);
         run("LDS replicated(+2)", k_lds_replicated, 4, out, cyc, threads);
         run("LDS plain256(+3)", k_lds_plain, 4, out, cyc, threads);
