@@ -151,6 +151,25 @@ int psd_scan_hist_correl(const uint32_t* yhist, int64_t n, int32_t bins, const u
 /* >= / <= compare producing u8 flags (content_detector.py:210, histogram_detector.py:108) */
 int psd_scan_compare(const double* values, int64_t n, double threshold, int32_t op /*0: >=, 1: <=, 2: <*/,
                      uint8_t* out_flags, void* stream);
+/* ---- cut state machines on the device.  Frame-number domain, constant frame
+ *      rate: `min_frames` is the host's conversion of min_scene_len (common.py:480-486,627-638).
+ *      cuts[cap] receives absolute frame numbers (first_frame + index), *count the number found
+ *      (may exceed cap: only cap are stored).  All pointers are DEVICE pointers. ---- */
+/* detector.py:160-224 FlashFilter over the `score >= threshold` flags; mode 0 = MERGE, 1 = SUPPRESS */
+int psd_cuts_flash_filter(const uint8_t* above, int64_t n, int64_t first_frame, int64_t min_frames,
+                          int32_t mode, int64_t* cuts, int32_t* count, int32_t cap, void* stream);
+/* adaptive_detector.py:134-143 (ratio from psd_scan_adaptive, NaN where the window is incomplete) */
+int psd_cuts_adaptive(const double* ratio, const double* score, int64_t n, int64_t first_frame,
+                      int32_t window_width, double adaptive_threshold, double min_content_val,
+                      int64_t min_frames, int64_t* cuts, int32_t* count, int32_t cap, void* stream);
+/* histogram_detector.py:87-112: cut where correl <= threshold and min_frames since the last cut */
+int psd_cuts_histogram(const double* correl, int64_t n, int64_t first_frame, double threshold,
+                       int64_t min_frames, int64_t* cuts, int32_t* count, int32_t cap, void* stream);
+/* threshold_detector.py:113-191: fade in/out automaton incl. the post_process final cut */
+int psd_cuts_threshold(const double* average, int64_t n, int64_t first_frame, double threshold,
+                       int32_t method_ceiling, double fade_bias, int64_t min_frames, int32_t add_final_scene,
+                       int64_t* cuts, int32_t* count, int32_t cap, void* stream);
+
 /* host-convenience wrappers: engine-owned sums -> host arrays (numpy), implies sync */
 int psd_engine_scan_content_host(psd_engine* e, int64_t first, int64_t n, const double weights[4],
                                  double weight_abs_sum, double* out_components,

@@ -355,7 +355,9 @@ class RefHistogramDetector:
             raise ValueError("Image must be 8-bit rgb for HistogramDetector")
         if frame_img.shape[2] != 3:
             raise ValueError("Image must have three color channels for HistogramDetector")
-        if not self._last_cut:  # NB: frame 0 is falsy (histogram_detector.py:87-88)
+        # histogram_detector.py:87-88 tests `not self._last_cut`; a FrameTimecode is always truthy
+        # (no __bool__/__len__), so this is an is-None check even for frame 0
+        if self._last_cut is None:
             self._last_cut = t
         hist = calculate_histogram(frame_img, bins=self._bins)
         if self._last_hist is not None:

@@ -95,6 +95,10 @@ SIGNATURES = {
     "psd_scan_average": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "psd_scan_hist_correl": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "psd_scan_compare": (C.c_int, [_vp, _i64, _dbl, _i32, _vp, _vp]),
+    "psd_cuts_flash_filter": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
+    "psd_cuts_adaptive": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _i64, _vp, _vp, _i32, _vp]),
+    "psd_cuts_histogram": (C.c_int, [_vp, _i64, _i64, _dbl, _i64, _vp, _vp, _i32, _vp]),
+    "psd_cuts_threshold": (C.c_int, [_vp, _i64, _i64, _dbl, _i32, _dbl, _i64, _i32, _vp, _vp, _i32, _vp]),
     "psd_engine_scan_content_host": (C.c_int, [_vp, _i64, _i64, _dp, _dbl, _vp, _vp]),
     "psd_engine_scan_adaptive_host": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "psd_engine_scan_average_host": (C.c_int, [_vp, _i64, _i64, _vp]),

@@ -46,7 +46,7 @@ class HistogramDetector(EngineDetector):
         diffs = self._engine.scan_hist_correl(self._bins, first=first, n=len(timecodes))
         cuts = []
         for i, timecode in enumerate(timecodes):
-            if not self._last_cut:  # NB falsy check as in histogram_detector.py:87-88
+            if not self._last_cut:  # histogram_detector.py:87-88 (a FrameTimecode is always truthy)
                 self._last_cut = timecode
             if (first + i) == self._base_index and not self._halo:
                 continue  # first frame: nothing to compare with yet

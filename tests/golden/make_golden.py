@@ -145,6 +145,8 @@ CASES = [
          mode="direct", stats=True, fps=30.0),
     dict(name="hist_256", gen=(260, 160, 90, 10, 20, 70, 30), det="histogram",
          kw=dict(bins=256, threshold=0.05), mode="direct", stats=True, fps=30.0),
+    dict(name="hist_256_minlen_edge", gen=(260, 160, 90, 10, 20, 70, 30), det="histogram",
+         kw=dict(bins=256, threshold=0.05, min_scene_len=22), mode="direct", stats=True, fps=30.0),
     dict(name="hist_100", gen=(200, 100, 60, 11, 20, 70, 29), det="histogram",
          kw=dict(bins=100, threshold=0.1, min_scene_len=0), mode="direct", stats=True, fps=30.0),
     # Through the reference SceneManager: auto-downscale (640x360 -> 256x144) + CSV.

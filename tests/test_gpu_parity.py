@@ -436,3 +436,39 @@ def test_scene_manager_plain_stream_crop_and_empty(lib):
     sm3.add_detector(ContentDetector())
     assert sm3.detect_scenes(_PlainStream(frames[:0])) == 0
     assert sm3.get_cut_list() == [] and sm3.get_scene_list() == []
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_device_cut_state_machines_match_golden(lib, name):
+    """scans + cut automata entirely on the device give the reference's cut list."""
+    from pyscenedetect_b200.device_cuts import DeviceCuts
+    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, Engine
+    case = get_case(name)
+    frames = case_frames(case)
+    kw = dict(case["kw"])
+    det = case["det"]
+    weights = tuple(kw.get("weights", (1.0, 1.0, 1.0, 0.0)))
+    if kw.get("luma_only"):
+        weights = (0.0, 0.0, 1.0, 0.0)
+    feats = {"content": F_HSV, "adaptive": F_HSV, "threshold": F_BGRSUM, "histogram": F_YHIST}[det]
+    if det in ("content", "adaptive") and weights[3] > 0.0:
+        feats |= F_EDGES
+    size = _scored_size(case) or (frames.shape[2], frames.shape[1])
+    eng = Engine(frames.shape[2], frames.shape[1], feats, width=size[0], height=size[1], max_batch=64,
+                 edge_kernel_size=kw.get("kernel_size") or 0)
+    eng.submit(frames)
+    dc = DeviceCuts(eng)
+    fps = case["fps"]
+    msl = kw.get("min_scene_len", 15)
+    if det == "content":
+        cuts = dc.content(weights, kw.get("threshold", 27.0), msl, fps, suppress=kw.get("filter_mode") == "SUPPRESS")
+    elif det == "adaptive":
+        cuts = dc.adaptive(weights, kw.get("adaptive_threshold", 3.0), msl, kw.get("window_width", 2),
+                           kw.get("min_content_val", 15.0), fps)
+    elif det == "histogram":
+        cuts = dc.histogram(kw.get("threshold", 0.20), kw.get("bins", 128), msl, fps)
+    else:
+        cuts = dc.threshold(kw.get("threshold", 12), msl, kw.get("fade_bias", 0.0), kw.get("add_final_scene", False),
+                            kw.get("method") == "CEILING", fps)
+    assert sorted(set(cuts)) == case["cuts"]
+    eng.close()
