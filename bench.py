@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -397,6 +397,14 @@ def run_ours(args):
         }
         if flags is not None:
             line["config"]["frames_above_threshold"] = int(flags.sum())
+        if world == 1 and args.detector == "content" and (sw, sh) == (W, H):
+            # whole detection on the device (scores -> flags -> FlashFilter automaton) vs the plan's
+            # ground-truth hard cuts; fades add extra cuts, so report both numbers
+            from pyscenedetect_b200.device_cuts import DeviceCuts
+            dev_cuts = DeviceCuts(eng).content(weights, 27.0, 15, 30.0)
+            truth = set(plan.cut_frames)
+            line["config"]["device_cut_list"] = {"cuts": len(dev_cuts), "ground_truth_hard_cuts": len(truth),
+                                                 "hard_cuts_found": len(truth & set(dev_cuts))}
 
     # ---- e2e: same metric through the public API with HOST buffers (rank-local shard) ----
     if not args.no_e2e:

@@ -472,3 +472,41 @@ def test_device_cut_state_machines_match_golden(lib, name):
                             kw.get("method") == "CEILING", fps)
     assert sorted(set(cuts)) == case["cuts"]
     eng.close()
+
+
+def test_independent_engines_in_threads(lib):
+    """SURVEY §8b threading contract: engines are single-producer but independent engines may run
+    concurrently (benchmark sweeps use one SceneManager per thread)."""
+    import threading
+
+    from pyscenedetect_b200.engine import F_BGRSUM, F_HSV, F_YHIST, Engine
+    rng = np.random.default_rng(11)
+    data = [rng.integers(0, 256, size=(24, 90, 160, 3), dtype=np.uint8) for _ in range(4)]
+    feats = F_HSV | F_BGRSUM | F_YHIST
+    want = []
+    for d in data:
+        e = Engine(160, 90, feats)
+        e.submit(d)
+        want.append((e.read_sums().tobytes(), e.read_yhist().tobytes()))
+        e.close()
+    got = [None] * 4
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                e = Engine(160, 90, feats, max_batch=8)
+                for j in range(0, 24, 5):
+                    e.submit(data[i][j:j + 5])
+                got[i] = (e.read_sums().tobytes(), e.read_yhist().tobytes())
+                e.close()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert got == want
