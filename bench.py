@@ -314,7 +314,9 @@ def run_ours(args):
         elif args.detector == "threshold":
             _capi.check(lib.psd_scan_average(sp, N, sw * sh * 3, d_val.data_ptr(), st))
         else:
-            _capi.check(lib.psd_scan_hist_correl(hp, N, 256, None, d_val.data_ptr(), st))
+            # the halo frame's histogram sits in the slot before stream frame 0 (psd_b200.h results layout)
+            prev_hist = (hp - 256 * 4) if (world > 1 and rank > 0) else None
+            _capi.check(lib.psd_scan_hist_correl(hp, N, 256, prev_hist, d_val.data_ptr(), st))
 
     ext_stream = torch.cuda.ExternalStream(eng.compute_stream, device=f"cuda:{dev}")
 
@@ -408,6 +410,9 @@ def run_ours(args):
 
     # ---- e2e: same metric through the public API with HOST buffers (rank-local shard) ----
     if not args.no_e2e:
+        from pyscenedetect_b200.engine import bind_host_to_gpu_numa_node
+        orig_affinity = os.sched_getaffinity(0)
+        numa = bind_host_to_gpu_numa_node(dev)  # page-locked frames on the GPU's own NUMA node
         ring = min(args.host_ring, N)
         pin = PinnedBuffer(ring * fbytes)
         _capi.check(lib.psd_memcpy_d2h(dev, pin.array.ctypes.data, frames_t.data_ptr(), ring * fbytes))
@@ -455,8 +460,10 @@ def run_ours(args):
                         if world == 1 else "sharding.detect_sharded(pinned host frames, TorchComm(nccl))"),
                 "host_frames": f"{ring} distinct page-locked frames cycled to {N} frames per step",
                 "cuts_found": n_cuts,
+                "host_numa": numa,
             }
         pin.close()
+        os.sched_setaffinity(0, orig_affinity)
 
     # ---- cpu_baseline: oracle port (the reference's cv2/numpy calls) on the host cores, N=1 only ----
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -78,6 +78,8 @@ int psd_device_count(void);
 /* name_out may be NULL; fills compute capability, SM count and total memory. */
 int psd_device_info(int device, char* name_out, size_t name_cap, int* cc_major, int* cc_minor,
                     int* sm_count, uint64_t* total_mem);
+/* PCI bus id "0000:3b:00.0" of a device (lets a host place page-locked buffers on the GPU's NUMA node) */
+int psd_device_pci_bus_id(int device, char* out, size_t cap);
 /* total kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t psd_launch_count(void);
 

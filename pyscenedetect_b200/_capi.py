@@ -65,6 +65,7 @@ SIGNATURES = {
     "psd_device_count": (C.c_int, []),
     "psd_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "psd_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t]),
     "psd_launch_count": (C.c_uint64, []),
     "psd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "psd_host_free": (C.c_int, [_vp]),

@@ -204,6 +204,12 @@ int psd_device_info(int device, char* name_out, size_t name_cap, int* cc_major, 
     return PSD_OK;
 }
 
+int psd_device_pci_bus_id(int device, char* out, size_t cap) {
+    PSD_REQUIRE(out && cap >= 16, "psd_device_pci_bus_id: buffer too small");
+    PSD_CUDA(cudaDeviceGetPCIBusId(out, (int)cap, device));
+    return PSD_OK;
+}
+
 int psd_host_alloc(size_t bytes, void** out) {
     PSD_REQUIRE(out && bytes > 0, "psd_host_alloc: bad args");
     PSD_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

@@ -238,6 +238,37 @@ class Engine:
         return out
 
 
+def bind_host_to_gpu_numa_node(device: int = 0) -> dict:
+    """Pin the calling process to the CPUs of the GPU's NUMA node so that page-locked staging
+    buffers allocated afterwards are local to the GPU's PCIe root (first-touch placement).  Returns
+    what was found; a no-op when the topology is not exposed."""
+    import os
+    lib = _capi.load()
+    buf = C.create_string_buffer(32)
+    check(lib.psd_device_pci_bus_id(device, buf, 32), "psd_device_pci_bus_id")
+    bdf = buf.value.decode().lower()
+    info = {"pci": bdf, "numa_node": None, "cpus": None}
+    base = f"/sys/bus/pci/devices/{bdf}"
+    try:
+        node = int(open(f"{base}/numa_node").read().strip())
+        info["numa_node"] = node
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if node >= 0 and allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except (OSError, ValueError):
+        pass
+    return info
+
+
 def synth_frames_device(dptr: int, params: np.ndarray, width: int, height: int,
                         frame_stride: int | None = None, device: int = 0):
     """Render ScenePlan rows straight into HBM (bit-exact twin of synth.render_frames)."""
@@ -247,5 +278,5 @@ def synth_frames_device(dptr: int, params: np.ndarray, width: int, height: int,
           "psd_synth_frames")
 
 
-__all__ = ["Engine", "PinnedBuffer", "DeviceBuffer", "synth_frames_device", "F_HSV", "F_BGRSUM",
+__all__ = ["Engine", "PinnedBuffer", "DeviceBuffer", "synth_frames_device", "bind_host_to_gpu_numa_node", "F_HSV", "F_BGRSUM",
            "F_YHIST", "F_EDGES"]

@@ -131,3 +131,36 @@ def test_plain_stream_crop_empty_host_logic(monkeypatch):
 
     monkeypatch.setattr(sm_mod, "PinnedBuffer", FakePinned)
     gpu_tests.test_scene_manager_plain_stream_crop_and_empty(None)
+
+
+def test_threshold_detector_uses_cached_metrics():
+    """threshold_detector.py:122-125: a metric already in the StatsManager wins over the computed one."""
+    import numpy as np
+
+    from pyscenedetect_b200 import FrameTimecode, StatsManager
+    from pyscenedetect_b200.detectors import ThresholdDetector
+    frames = np.full((40, 36, 64, 3), 100, np.uint8)   # constant brightness: no fades on its own
+    stats = StatsManager()
+    det = ThresholdDetector(min_scene_len=5)
+    det.stats_manager = stats
+    stats.register_metrics(det.get_metrics())
+    for t in range(10, 20):                           # cached "dark" stretch => fade out / fade in
+        stats.set_metrics(FrameTimecode(t, 30.0), {"average_rgb": 3.0})
+    cuts = []
+    for t in range(40):
+        cuts += det.process_frame(FrameTimecode(t, 30.0), frames[t])
+    assert [c.frame_num for c in cuts] == [15]        # f_out=10, fade in at 20 -> 10 + round(10*1/2)
+    assert stats.get_metrics(FrameTimecode(12, 30.0), ["average_rgb"]) == [3.0]
+    assert float(stats.get_metrics(FrameTimecode(30, 30.0), ["average_rgb"])[0]) == 100.0
+
+
+def test_adaptive_event_buffer_and_metric_keys():
+    from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector, ThresholdDetector
+    a = AdaptiveDetector(window_width=4, luma_only=True)
+    assert a.event_buffer_length == 4
+    assert a.get_metrics() == ["content_val", "delta_hue", "delta_sat", "delta_lum", "delta_edges",
+                               "adaptive_ratio_lum (w=4)"]
+    assert ContentDetector(min_scene_len=15).event_buffer_length == 15
+    assert ContentDetector(min_scene_len=0.5).event_buffer_length == 120     # ceil(0.5 * 240)
+    assert HistogramDetector(bins=64).get_metrics() == ["hist_diff [bins=64]"]
+    assert ThresholdDetector().get_metrics() == ["average_rgb"]
