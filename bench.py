@@ -195,7 +195,8 @@ def run_reference(args):
     # The numpy temporaries of _mean_pixel_distance make this path memory/allocator bound, so
     # "all hardware threads" is not always the fastest process count: probe a few counts on a
     # short round and keep the best one for the timed steps (the CPU gets its best shot).
-    candidates = sorted({max(1, cores // d) for d in (1, 2, 4, 8)} | {min(cores, 16)}, reverse=True)
+    candidates = sorted({max(1, cores // d) for d in (1, 2, 4, 8)} | {min(cores, c) for c in (8, 12, 16, 24, 48)},
+                        reverse=True)
     probe = {}
     for p in candidates:
         probe[p] = p * 4 / _ref_run_pool(args.detector, p, 4, args.width, args.height, args.seed, 1)[0]

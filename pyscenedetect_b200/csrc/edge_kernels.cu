@@ -158,18 +158,29 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
         if (tid == 0) dirty_cur[tile_id] = 0;
         return;
     }
-    volatile uint8_t(*vt)[HTX + 4] = t;
+    // compact the weak pixels of the tile once; the fix-point loop then only visits those
+    __shared__ uint16_t weak_list[HTX * HTY];
+    __shared__ int n_weak;
+    if (tid == 0) n_weak = 0;
+    __syncthreads();
+    for (int i = tid; i < HTX * HTY; i += 256) {
+        const int ly = 1 + i / HTX, lx = 1 + (i % HTX);
+        if (t[ly][lx] == 1) weak_list[atomicAdd(&n_weak, 1)] = (uint16_t)(ly * (HTX + 4) + lx);
+    }
+    __syncthreads();
+    const int nw = n_weak;
+    volatile uint8_t* vt = &t[0][0];
+    constexpr int S = HTX + 4;  // row stride of the tile
     int tile_changed = 0;
     while (true) {
         int ch = 0;
-        for (int i = tid; i < HTX * HTY; i += 256) {
-            const int ly = 1 + i / HTX, lx = 1 + (i % HTX);
-            if (vt[ly][lx] == 1) {
-                const bool s = vt[ly - 1][lx - 1] == 2 || vt[ly - 1][lx] == 2 || vt[ly - 1][lx + 1] == 2 ||
-                               vt[ly][lx - 1] == 2 || vt[ly][lx + 1] == 2 || vt[ly + 1][lx - 1] == 2 ||
-                               vt[ly + 1][lx] == 2 || vt[ly + 1][lx + 1] == 2;
+        for (int i = tid; i < nw; i += 256) {
+            const int p = weak_list[i];
+            if (vt[p] == 1) {
+                const bool s = vt[p - S - 1] == 2 || vt[p - S] == 2 || vt[p - S + 1] == 2 || vt[p - 1] == 2 ||
+                               vt[p + 1] == 2 || vt[p + S - 1] == 2 || vt[p + S] == 2 || vt[p + S + 1] == 2;
                 if (s) {
-                    vt[ly][lx] = 2;
+                    vt[p] = 2;
                     ch = 1;
                 }
             }

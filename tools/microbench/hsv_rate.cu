@@ -4,11 +4,52 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hsv_rate hsv_rate.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <math.h>
 
 #include "../../pyscenedetect_b200/csrc/hsv_math.cuh"
 
 using namespace psd;
 constexpr int ITERS = 2048;
+
+// ---- experiment: table lookups through the texture unit instead of the replicated smem LUT ----
+__device__ __forceinline__ void hsv_px_tex(const uint32_t (&w)[12], int KB, cudaTextureObject_t ts,
+                                           cudaTextureObject_t th, uint32_t& oh, uint32_t& os, uint32_t& ov);
+template <int KB>
+__device__ __forceinline__ void hsv_px_v7(const uint32_t (&w)[12], cudaTextureObject_t ts, cudaTextureObject_t th,
+                                          uint32_t& oh, uint32_t& os, uint32_t& ov) {
+    const float B = magic_byte_dp4a<(KB + 0) & 3>(w[(KB + 0) >> 2]);
+    const float G = magic_byte<(KB + 1) & 3>(w[(KB + 1) >> 2]);
+    const float R = magic_byte_dp4a<(KB + 2) & 3>(w[(KB + 2) >> 2]);
+    const float V = fmax3(B, G, R);
+    const float mn = fmin3(B, G, R);
+    const float d = V - mn;
+    const float sdivp = tex1D<float>(ts, V - 8388608.0f);
+    const float hdivp = tex1D<float>(th, d);
+    const float yS = fma_rz(d, sdivp, 32768.5f);
+    const float hR = G - B;
+    const float hG = fmaf(d, 2.0f, B - R);
+    const float hB = fmaf(d, 4.0f, R - G);
+    const float h = (V == R) ? hR : ((V == G) ? hG : hB);
+    float yH = fma_rm(h, hdivp, 49152.5f);
+    yH = fmaf(fma_sat(yH, -256.0f, 12582912.0f), 180.0f, yH);
+    oh = __float_as_uint(yH);
+    os = __float_as_uint(yS);
+    ov = __float_as_uint(V);
+}
+__device__ __forceinline__ void hsv16_v7(const uint32_t (&w)[12], Px16& o, cudaTextureObject_t ts, cudaTextureObject_t th) {
+    uint32_t h[16], s[16], v[16];
+#define PSD_PX(i) hsv_px_v7<3 * (i)>(w, ts, th, h[i], s[i], v[i]);
+    PSD_PX(0) PSD_PX(1) PSD_PX(2) PSD_PX(3) PSD_PX(4) PSD_PX(5) PSD_PX(6) PSD_PX(7)
+    PSD_PX(8) PSD_PX(9) PSD_PX(10) PSD_PX(11) PSD_PX(12) PSD_PX(13) PSD_PX(14) PSD_PX(15)
+#undef PSD_PX
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o.h[j] = __byte_perm(__byte_perm(h[4 * j], h[4 * j + 1], 0x0051), __byte_perm(h[4 * j + 2], h[4 * j + 3], 0x0051), 0x5410);
+        o.s[j] = __byte_perm(__byte_perm(s[4 * j], s[4 * j + 1], 0x0051), __byte_perm(s[4 * j + 2], s[4 * j + 3], 0x0051), 0x5410);
+        o.v[j] = __byte_perm(__byte_perm(v[4 * j], v[4 * j + 1], 0x0040), __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x0040), 0x5410);
+    }
+}
+__device__ cudaTextureObject_t g_ts, g_th;
 
 template <int VARIANT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint32_t seed, long long* cyc) {
@@ -36,7 +77,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
         Px16 cur;
-        if (VARIANT == 6)
+        if (VARIANT == 7)
+            hsv16_v7(w, cur, g_ts, g_th);
+        else if (VARIANT == 6)
             hsv16_v4pair(w, cur, lv);
         else if (VARIANT == 4)
             hsv16_v4(w, cur, lv);
@@ -77,7 +120,28 @@ void run(uint32_t* out, long long* cyc) {
            err == cudaSuccess ? "" : cudaGetErrorString(err));
 }
 
+static cudaTextureObject_t make_tex(const float* host) {
+    cudaArray_t arr;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+    cudaMallocArray(&arr, &cd, 256);
+    cudaMemcpy2DToArray(arr, 0, 0, host, 256 * sizeof(float), 256 * sizeof(float), 1, cudaMemcpyHostToDevice);
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+    cudaTextureDesc td{}; td.addressMode[0] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    cudaTextureObject_t t = 0; cudaCreateTextureObject(&t, &rd, &td, nullptr);
+    return t;
+}
+
 int main() {
+    {
+        float hs[256], hh[256];
+        for (int i = 0; i < 256; ++i) {
+            hs[i] = i ? (float)nearbyint(1044480.0 / i) / 4096.0f : 0.0f;
+            hh[i] = i ? (float)nearbyint(737280.0 / (6.0 * i)) / 4096.0f : 0.0f;
+        }
+        cudaTextureObject_t ts = make_tex(hs), th = make_tex(hh);
+        cudaMemcpyToSymbol(g_ts, &ts, sizeof(ts)); cudaMemcpyToSymbol(g_th, &th, sizeof(th));
+    }
     uint32_t* out; long long* cyc;
     cudaMalloc(&out, 148 * 3 * 1024 * 4); cudaMalloc(&cyc, 148 * 3 * 8);
     run<0, 256, 3>(out, cyc);
@@ -88,5 +152,8 @@ int main() {
     printf("PSD_V4_PRMT_CHANNELS=%d\n", PSD_V4_PRMT_CHANNELS);
     run<4, 768, 1>(out, cyc);
     run<6, 768, 1>(out, cyc);
+    run<7, 768, 1>(out, cyc);
+    run<7, 256, 3>(out, cyc);
+    run<7, 512, 2>(out, cyc);
     return 0;
 }
