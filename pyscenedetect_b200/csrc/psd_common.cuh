@@ -62,6 +62,7 @@ struct ScoreArgs {
     uint32_t* yhist;         // [n][256] (pre-zeroed) or nullptr
     uint32_t* vhist;         // [n][256] (pre-zeroed) or nullptr
     uint8_t* vplane;         // [n][n_pixels] or nullptr
+    uint32_t shift24;        // 0x01000000, passed at run time (hsv_half2.cuh, PSD_V7_ADDR 1)
 };
 int launch_score(const ScoreArgs& a, uint32_t features, int variant, cudaStream_t stream);
 int score_kernel_smem_bytes();

@@ -13,6 +13,7 @@
 // red.global.add.u64 per CTA per frame per channel, so results are order-independent integers
 // and identical for any batching / sharding.
 #include "hsv_math.cuh"
+#include "hsv_half2.cuh"
 #include "psd_common.cuh"
 
 namespace psd {
@@ -326,7 +327,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <uint32_t F>
+// HV selects the HSV arithmetic: 4 = scalar float LUT formulation (hsv_math.cuh), 7 = pixel pairs in
+// half2 / u16x2 lanes (hsv_half2.cuh).  Both are bit-exact; 7 needs ~20 % fewer issue slots.
+template <uint32_t F, int HV>
 __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
@@ -358,7 +361,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         (&sm.vhist[0][0])[i] = 0;
     }
     if (tid < kWsStages * 8) (&sm.acc[0][0])[tid] = 0;
-    if (kHSV) lut_fill(sm.lut, tid, kWsThreads);
+    if (kHSV) {
+        if (HV >= 7) lut_fill7(sm.lut, tid, kWsThreads);
+        else lut_fill(sm.lut, tid, kWsThreads);
+    }
     if (tid == 0) {
         for (int s = 0; s < kWsStages; ++s) {
             mbar_init(&sm.full[s], 1);
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     LutView lut{0u, 0u};
     lut.s_addr = smem_u32(sm.lut) + lane * 4;
     lut.h_addr = lut.s_addr + 128;
+    const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
     Px16 prev;
 #pragma unroll
     for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
@@ -447,7 +454,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
             hsv16_v4pair(w, cur, lut);  // FADD2/FFMA2 on pixel pairs: 12 % fewer issue slots, but measured
                                         // 1 % slower in the kernel and 5 % slower compute-only (pipe-bound)
 #else
-            hsv16_v4(w, cur, lut);
+            if (HV >= 7) hsv16_v7<HV == 8>(w, cur, lut7, a.shift24);
+            else hsv16_v4(w, cur, lut);
 #endif
             if (prev_valid) {
 #pragma unroll
@@ -503,22 +511,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     }
 }
 
-template <uint32_t F>
+template <uint32_t F, int HV>
 static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
     const int smem = (int)sizeof(WsSmem);
-    PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    a.shift24 = 0x01000000u;
     a.n_strips = n_ws_strips;
     const int64_t grid = (int64_t)a.n_chunks * n_ws_strips;
     PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
-    psd_score_ws_kernel<F><<<(unsigned)grid, kWsThreads, smem, stream>>>(a);
+    psd_score_ws_kernel<F, HV><<<(unsigned)grid, kWsThreads, smem, stream>>>(a);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;
 }
 
-static int dispatch_ws(const ScoreArgs& a, uint32_t f, int n_ws_strips, cudaStream_t s) {
+static int dispatch_ws(const ScoreArgs& a, uint32_t f, int hv, int n_ws_strips, cudaStream_t s) {
     switch (f & 15u) {
-#define CASE(F) case F: return launch_ws<F>(a, n_ws_strips, s);
+        // masks without the HSV bit do not depend on HV: one instantiation
+#define CASE(F) case F: if (!((F) & PSD_F_HSV) || hv == 4) return launch_ws<F, 4>(a, n_ws_strips, s); \
+                        return hv == 8 ? launch_ws<F, 8>(a, n_ws_strips, s) : launch_ws<F, 7>(a, n_ws_strips, s);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
         CASE(9) CASE(11) CASE(13) CASE(15)
 #undef CASE
@@ -572,7 +583,7 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     a.tma_ok = ((al & 15) == 0) ? 1 : 0;
     a.px_base = 0;
     a.write_has_prev = 1;
-    if (variant == 5) {
+    if (variant == 5 || variant == 7 || variant == 8) {
         // warp-specialised kernel on the 12288-pixel strips, generic kernel (variant 2) on
         // the remainder; an unaligned input goes entirely through the generic kernel
         int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
@@ -583,7 +594,7 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
             covered = a.n_pixels;
         }
         if (n_ws > 0) {
-            int rc = dispatch_ws(a, features, n_ws, stream);
+            int rc = dispatch_ws(a, features, variant == 5 ? 4 : variant, n_ws, stream);
             if (rc) return rc;
             a.px_base = covered;
             a.write_has_prev = 0;
@@ -600,7 +611,7 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
         case 2: return dispatch<2>(a, features, stream);
         case 4: return dispatch<4>(a, features, stream);
         default:
-            set_error("hsv variant %d is not built into the score kernel (1, 2, 4, 5 are)", variant);
+            set_error("hsv variant %d is not built into the score kernel (1, 2, 4, 5, 7, 8 are)", variant);
             return PSD_ERR_INVALID;
     }
 }
@@ -608,7 +619,7 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
 // ---- test hook: the same device functions on a flat pixel array ----
 template <int VARIANT>
 __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_t* h, uint8_t* s,
-                                    uint8_t* v, uint8_t* y) {
+                                    uint8_t* v, uint8_t* y, uint32_t shift24) {
     extern __shared__ __align__(128) float lutmem[];
     __shared__ int32_t sdiv[256], hdiv[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -616,11 +627,13 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
     }
     LutView lut{0u, 0u};
+    if (VARIANT == 7 || VARIANT == 8) lut_fill7(lutmem, threadIdx.x, blockDim.x);
     if (VARIANT == 4 || VARIANT == 6) {
         lut_fill(lutmem, threadIdx.x, blockDim.x);
         lut.s_addr = smem_u32(lutmem) + (threadIdx.x & 31) * 4;
         lut.h_addr = lut.s_addr + 128;
     }
+    const LutView7 lut7 = make_lut7(smem_u32(lutmem), threadIdx.x & 31);
     __syncthreads();
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
          g += (int64_t)gridDim.x * blockDim.x) {
@@ -631,7 +644,9 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
         w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
         Px16 o;
-        if (VARIANT == 6)
+        if (VARIANT == 7 || VARIANT == 8)
+            hsv16_v7<VARIANT == 8>(w, o, lut7, shift24);
+        else if (VARIANT == 6)
             hsv16_v4pair(w, o, lut);
         else if (VARIANT == 4)
             hsv16_v4(w, o, lut);
@@ -648,10 +663,10 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
 template <int VARIANT>
 static int run_test_hsv(const uint8_t* d_bgr, int64_t groups, uint8_t* dh, uint8_t* ds, uint8_t* dv,
                         uint8_t* dy) {
-    const int smem = (VARIANT == 4 || VARIANT == 6) ? 65536 : 0;
+    const int smem = (VARIANT == 4 || VARIANT >= 6) ? 65536 : 0;
     PSD_CUDA(cudaFuncSetAttribute(psd_test_hsv_kernel<VARIANT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    psd_test_hsv_kernel<VARIANT><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy);
+    psd_test_hsv_kernel<VARIANT><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy, 0x01000000u);
     PSD_CHECK_LAUNCH();
     return PSD_OK;
 }
@@ -662,7 +677,7 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
                             uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
     using namespace psd;
     PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
-    PSD_REQUIRE((variant >= 0 && variant <= 4) || variant == 6, "unknown hsv variant %d", variant);
+    PSD_REQUIRE((variant >= 0 && variant <= 4) || (variant >= 6 && variant <= 8), "unknown hsv variant %d", variant);
     PSD_CUDA(cudaSetDevice(device));
     uint8_t *d_bgr = nullptr, *d_out = nullptr;
     PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
@@ -679,6 +694,8 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
         case 2: rc = run_test_hsv<2>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
         case 3: rc = run_test_hsv<3>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
         case 4: rc = run_test_hsv<4>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 7: rc = run_test_hsv<7>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
+        case 8: rc = run_test_hsv<8>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
         default: rc = run_test_hsv<6>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
     }
     if (rc) return rc;

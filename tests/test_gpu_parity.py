@@ -122,7 +122,7 @@ def test_batched_scene_manager_matches_reference_golden(lib, name, batch):
         _check_stats(case, stats, frames.shape[0])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 7, 8])
 def test_hsv_and_y_exhaustive_2_24(lib, variant):
     """Every BGR colour through the device functions of the fused kernel vs cv2."""
     v = np.arange(1 << 24, dtype=np.uint32)
@@ -311,7 +311,7 @@ def test_kernel_variants_agree_at_full_size(lib, shape, monkeypatch):
     buf = DeviceBuffer(n * w * h * 3)
     synth_frames_device(buf.ptr, plan.params, w, h)
     ref = None
-    for variant in ("5", "4", "2", "1"):
+    for variant in ("5", "7", "8", "4", "2", "1"):
         monkeypatch.setenv("PSD_HSV_VARIANT", variant)
         eng = Engine(w, h, F_HSV | F_BGRSUM | F_YHIST, max_batch=128)
         eng.submit_device(buf.ptr, n)

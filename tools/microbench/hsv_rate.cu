@@ -4,9 +4,11 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hsv_rate hsv_rate.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "../../pyscenedetect_b200/csrc/hsv_math.cuh"
+#include "../../pyscenedetect_b200/csrc/hsv_half2.cuh"
 
 using namespace psd;
 constexpr int ITERS = 2048;
@@ -15,7 +17,7 @@ constexpr int ITERS = 2048;
 __device__ __forceinline__ void hsv_px_tex(const uint32_t (&w)[12], int KB, cudaTextureObject_t ts,
                                            cudaTextureObject_t th, uint32_t& oh, uint32_t& os, uint32_t& ov);
 template <int KB>
-__device__ __forceinline__ void hsv_px_v7(const uint32_t (&w)[12], cudaTextureObject_t ts, cudaTextureObject_t th,
+__device__ __forceinline__ void hsv_px_tex1(const uint32_t (&w)[12], cudaTextureObject_t ts, cudaTextureObject_t th,
                                           uint32_t& oh, uint32_t& os, uint32_t& ov) {
     const float B = magic_byte_dp4a<(KB + 0) & 3>(w[(KB + 0) >> 2]);
     const float G = magic_byte<(KB + 1) & 3>(w[(KB + 1) >> 2]);
@@ -36,9 +38,9 @@ __device__ __forceinline__ void hsv_px_v7(const uint32_t (&w)[12], cudaTextureOb
     os = __float_as_uint(yS);
     ov = __float_as_uint(V);
 }
-__device__ __forceinline__ void hsv16_v7(const uint32_t (&w)[12], Px16& o, cudaTextureObject_t ts, cudaTextureObject_t th) {
+__device__ __forceinline__ void hsv16_tex(const uint32_t (&w)[12], Px16& o, cudaTextureObject_t ts, cudaTextureObject_t th) {
     uint32_t h[16], s[16], v[16];
-#define PSD_PX(i) hsv_px_v7<3 * (i)>(w, ts, th, h[i], s[i], v[i]);
+#define PSD_PX(i) hsv_px_tex1<3 * (i)>(w, ts, th, h[i], s[i], v[i]);
     PSD_PX(0) PSD_PX(1) PSD_PX(2) PSD_PX(3) PSD_PX(4) PSD_PX(5) PSD_PX(6) PSD_PX(7)
     PSD_PX(8) PSD_PX(9) PSD_PX(10) PSD_PX(11) PSD_PX(12) PSD_PX(13) PSD_PX(14) PSD_PX(15)
 #undef PSD_PX
@@ -60,6 +62,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
         hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
     }
     LutView lv{0, 0};
+    const LutView7 lv7 = make_lut7((uint32_t)__cvta_generic_to_shared(lut), threadIdx.x & 31);
+    if (VARIANT == 7 || VARIANT == 8) lut_fill7(lut, threadIdx.x, blockDim.x);
     if (VARIANT == 4 || VARIANT == 6) {
         lut_fill(lut, threadIdx.x, blockDim.x);
         lv.s_addr = (uint32_t)__cvta_generic_to_shared(lut) + (threadIdx.x & 31) * 4;
@@ -77,8 +81,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
         Px16 cur;
-        if (VARIANT == 7)
-            hsv16_v7(w, cur, g_ts, g_th);
+        if (VARIANT == 17)
+            hsv16_tex(w, cur, g_ts, g_th);
+        else if (VARIANT == 7 || VARIANT == 8)
+            hsv16_v7<VARIANT == 8>(w, cur, lv7, seed << 11);  // 12345 << 11 is not 2^24, irrelevant for the rate
         else if (VARIANT == 6)
             hsv16_v4pair(w, cur, lv);
         else if (VARIANT == 4)
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rate_kernel(uint32_t* out, uint
 template <int VARIANT, int THREADS, int MINB>
 void run(uint32_t* out, long long* cyc) {
     const int grid = 148 * MINB;
-    const int smem = (VARIANT == 4 || VARIANT == 6) ? 65536 : 0;
+    const int smem = (VARIANT == 4 || VARIANT == 6 || VARIANT == 7 || VARIANT == 8) ? 65536 : 0;
     cudaFuncSetAttribute(rate_kernel<VARIANT, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     rate_kernel<VARIANT, THREADS, MINB><<<grid, THREADS, smem>>>(out, 12345u, cyc);
     cudaDeviceSynchronize();
@@ -144,16 +150,21 @@ int main() {
     }
     uint32_t* out; long long* cyc;
     cudaMalloc(&out, 148 * 3 * 1024 * 4); cudaMalloc(&cyc, 148 * 3 * 8);
-    run<0, 256, 3>(out, cyc);
-    run<1, 256, 3>(out, cyc);
-    run<2, 256, 3>(out, cyc);
-    run<3, 256, 3>(out, cyc);
-    run<2, 256, 2>(out, cyc);
+    if (getenv("HSV_RATE_ALL")) {
+        run<0, 256, 3>(out, cyc);
+        run<1, 256, 3>(out, cyc);
+        run<2, 256, 3>(out, cyc);
+        run<3, 256, 3>(out, cyc);
+        run<2, 256, 2>(out, cyc);
+        run<17, 768, 1>(out, cyc);
+    }
     printf("PSD_V4_PRMT_CHANNELS=%d\n", PSD_V4_PRMT_CHANNELS);
     run<4, 768, 1>(out, cyc);
     run<6, 768, 1>(out, cyc);
+    printf("PSD_V7_ADDR=%d PSD_V7_HMNMX=%d\n", PSD_V7_ADDR, PSD_V7_HMNMX);
     run<7, 768, 1>(out, cyc);
-    run<7, 256, 3>(out, cyc);
-    run<7, 512, 2>(out, cyc);
+    run<8, 768, 1>(out, cyc);
+    run<7, 512, 1>(out, cyc);
+    run<8, 1024, 1>(out, cyc);
     return 0;
 }
