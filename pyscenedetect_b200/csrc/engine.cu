@@ -311,7 +311,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
     e->src_frame_bytes = (int64_t)e->sw * e->sh * 3;
     e->features = cfg->features | ((cfg->features & PSD_F_EDGES) ? PSD_F_HSV : 0);
     e->max_batch = cfg->max_batch;
-    e->variant = 5;  // warp-specialised LUT kernel + generic remainder (score_kernel.cu)
+    e->variant = 7;  // warp-specialised kernel with the pixel-pair HSV arithmetic + generic remainder (score_kernel.cu)
     if (const char* v = getenv("PSD_HSV_VARIANT")) e->variant = atoi(v);
     if (e->features & PSD_F_EDGES) {
         int k = cfg->edge_kernel_size;

@@ -306,10 +306,16 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 // 24 consumer warps = 6 per sub-partition (25 was measured 4.5 % slower: 7/6/6/6 is unbalanced).
 // A last, partial strip is handled in the same kernel when it is a whole number of 16-pixel
 // thread slices (1080p: 168 full strips + one of 9216 px); other remainders go to the generic kernel.
-constexpr int kWsConsumerWarps = 24;
+#ifndef PSD_WS_WARPS
+#define PSD_WS_WARPS 24
+#endif
+#ifndef PSD_WS_STAGES
+#define PSD_WS_STAGES 3
+#endif
+constexpr int kWsConsumerWarps = PSD_WS_WARPS;
 constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
 constexpr int kWsThreads = kWsConsumers + 32;        // + producer warp
-constexpr int kWsStages = 3;
+constexpr int kWsStages = PSD_WS_STAGES;
 constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12288 pixels
 constexpr int kWsStripBytes = kWsStripPx * 3;            // 36864 bytes
 
@@ -318,10 +324,39 @@ struct __align__(128) WsSmem {
     float lut[256 * 64];
     unsigned long long full[kWsStages];
     unsigned long long empty[kWsStages];
-    uint32_t acc[kWsStages][8];
+    // per-lane running totals of sadH, sadS, sadV, bgr: every consumer thread adds its partial to the
+    // word of ITS lane (32 distinct banks: one conflict-free red.shared per channel per thread, no
+    // warp reduction, no election).  Never zeroed: the producer keeps the totals it saw last and
+    // flushes the difference, so its bookkeeping needs no ordering against the consumers' adds.
+    uint32_t accl[kWsStages][4][32];
+    uint32_t accl_seen[kWsStages][4][32];
     uint32_t yhist[kWsStages][256];
     uint32_t vhist[kWsStages][256];
 };
+
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase
+// completes instead of burning issue slots of its sub-partition in a poll loop
+__device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -360,7 +395,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         (&sm.yhist[0][0])[i] = 0;
         (&sm.vhist[0][0])[i] = 0;
     }
-    if (tid < kWsStages * 8) (&sm.acc[0][0])[tid] = 0;
+    for (int i = tid; i < kWsStages * 4 * 32; i += kWsThreads) {
+        (&sm.accl[0][0][0])[i] = 0;
+        (&sm.accl_seen[0][0][0])[i] = 0;
+    }
     if (kHSV) {
         if (HV >= 7) lut_fill7(sm.lut, tid, kWsThreads);
         else lut_fill(sm.lut, tid, kWsThreads);
@@ -382,18 +420,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
                 bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), copy_bytes, &sm.full[s]);
             }
         }
+        int stage = 0;
+        uint32_t parity = 0;
         for (int it = it_begin; it < it_end; ++it) {
-            const int k = it - it_begin;
-            const int stage = k % kWsStages;
-            mbar_wait(&sm.empty[stage], (uint32_t)((k / kWsStages) & 1));
+            mbar_wait_hint(&sm.empty[stage], parity);
             const int fi = f0 - 1 + it;
+            // the per-lane totals are read BEFORE the stage is re-armed: no consumer can add the next
+            // frame of this stage to them until the copy issued below has landed
+            uint32_t tot[4] = {0u, 0u, 0u, 0u};
+            if (it >= 1 && (kHSV || kSUM)) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if ((c < 3 && kHSV) || (c == 3 && kSUM)) tot[c] = sm.accl[stage][c][lane];
+            }
             if (it >= 1) {  // this CTA accounts for frame fi (not the halo)
-                if (lane < 4) {
-                    const uint32_t v = sm.acc[stage][lane];
-                    sm.acc[stage][lane] = 0;
-                    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fi]) + (lane < 3 ? lane : 4),
-                                     (unsigned long long)v);
-                }
                 if (kYH) {
 #pragma unroll
                     for (int b = lane; b < 256; b += 32) {
@@ -411,11 +451,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
                 if (a.write_has_prev && strip == 0 && lane == 0)
                     a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
             }
-            __syncwarp();  // the zeroing above is ordered before lane 0 re-arms the stage
+            __syncwarp();  // the histogram zeroing above is ordered before lane 0 re-arms the stage
             if (lane == 0 && it + kWsStages < it_end) {
                 mbar_expect_tx(&sm.full[stage], copy_bytes);
                 bulk_g2s(sm.ring[stage], frame_ptr(it + kWsStages), copy_bytes, &sm.full[stage]);
             }
+            if (it >= 1 && (kHSV || kSUM)) {  // after the re-arm: the copy engine's queue is fed first
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if ((c < 3 && !kHSV) || (c == 3 && !kSUM)) continue;
+                    const uint32_t d = tot[c] - sm.accl_seen[stage][c][lane];
+                    sm.accl_seen[stage][c][lane] = tot[c];
+                    const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, d);
+                    if (lane == 0 && v)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(&a.sums[fi]) + (c < 3 ? c : 4),
+                                  (unsigned long long)v);
+                }
+            }
+            if (++stage == kWsStages) { stage = 0; parity ^= 1u; }
         }
         return;
     }
@@ -425,31 +478,34 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     lut.s_addr = smem_u32(sm.lut) + lane * 4;
     lut.h_addr = lut.s_addr + 128;
     const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
-    Px16 prev;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) prev.h[j] = prev.s[j] = prev.v[j] = 0;
-    bool prev_valid = false;
     const int my_px = px0 + tid * kPxPerThread;
     const bool active = tid * kPxPerThread < valid_px;  // only the last strip has idle threads
+    const uint32_t accl_addr = smem_u32(&sm.accl[0][0][lane]);
+    const uint32_t ring_addr = smem_u32(sm.ring[0]) + tid * 48;
+    bool prev_valid = false;
+    int stage = 0;
+    uint32_t parity = 0;
+    // a zero the compiler cannot see through: it stays in one register for the whole loop instead of
+    // being re-materialised (CS2R) in front of every accumulation chain
+    const uint32_t zero = a.shift24 ^ 0x01000000u;
 
-    for (int it = it_begin; it < it_end; ++it) {
-        const int k = it - it_begin;
-        const int stage = k % kWsStages;
-        mbar_wait(&sm.full[stage], (uint32_t)((k / kWsStages) & 1));
+    // One frame: wait for the stage, pull this thread's 48 bytes, score them against `prev`, leave the
+    // planes in `cur`.  Called alternately with (P0, P1) and (P1, P0), so the previous frame's planes
+    // never have to be copied between registers.
+    auto step = [&](const int it, const Px16& prev, Px16& cur) {
+        mbar_wait_hint(&sm.full[stage], parity);
         uint32_t w[12];
-        {
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            const uint4* p = reinterpret_cast<const uint4*>(sm.ring[stage] + tid * 48);
-            const uint4 q0 = active ? p[0] : z, q1 = active ? p[1] : z, q2 = active ? p[2] : z;
-            w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
-            w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
-            w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+        {   // idle threads of a partial last strip read stale ring bytes; they never contribute (see `mine`)
+            const uint32_t ra = ring_addr + stage * kWsStripBytes;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ra));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(ra));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]) : "r"(ra));
         }
         const int fi = f0 - 1 + it;
         const bool own = (it >= 1);
-        uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
+        const bool mine = own && active;
+        const uint32_t acc_stage = accl_addr + stage * (4 * 32 * 4);
         if (kHSV) {
-            Px16 cur;
 #ifdef PSD_WS_PAIR_V4
             hsv16_v4pair(w, cur, lut);  // FADD2/FFMA2 on pixel pairs: 12 % fewer issue slots, but measured
                                         // 1 % slower in the kernel and 5 % slower compute-only (pipe-bound)
@@ -457,17 +513,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
             if (HV >= 7) hsv16_v7<HV == 8>(w, cur, lut7, a.shift24);
             else hsv16_v4(w, cur, lut);
 #endif
-            if (prev_valid) {
+            if (prev_valid && mine) {
+                // one dependent VABSDIFF4.ACC chain per plane (the compiler otherwise splits each into
+                // four zero-seeded accumulators plus an IADD3 tree: 12 extra issue slots per frame)
+                uint32_t sad_h = sad4_acc(cur.h[0], prev.h[0], zero), sad_s = sad4_acc(cur.s[0], prev.s[0], zero),
+                         sad_v = sad4_acc(cur.v[0], prev.v[0], zero);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sad_h = __vsadu4(cur.h[j], prev.h[j]) + sad_h;
-                    sad_s = __vsadu4(cur.s[j], prev.s[j]) + sad_s;
-                    sad_v = __vsadu4(cur.v[j], prev.v[j]) + sad_v;
+                for (int j = 1; j < 4; ++j) {
+                    sad_h = sad4_acc(cur.h[j], prev.h[j], sad_h);
+                    sad_s = sad4_acc(cur.s[j], prev.s[j], sad_s);
+                    sad_v = sad4_acc(cur.v[j], prev.v[j], sad_v);
                 }
+                red_shared_add(acc_stage, sad_h);
+                red_shared_add(acc_stage + 128, sad_s);
+                red_shared_add(acc_stage + 256, sad_v);
             }
-            prev = cur;
             prev_valid = true;
-            if (kEDGE && own && active) {
+            if (kEDGE && mine) {
                 uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
                 if ((a.n_pixels & 15) == 0) {
                     *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
@@ -479,36 +541,36 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
                     atomicAdd(&sm.vhist[stage][(cur.v[p >> 2] >> ((p & 3) * 8)) & 0xFF], 1u);
             }
         }
-        if (own) {
+        if (mine) {
             if (kSUM) {
+                uint32_t bsum = 0;
 #pragma unroll
                 for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
+                red_shared_add(acc_stage + 384, bsum);
             }
-            if (kYH && active) {
+            if (kYH) {
                 uint32_t* hist = sm.yhist[stage];
 #define PSD_YH(i) atomicAdd(&hist[y_of_pixel<i>(w)], 1u);
                 PSD_YH(0) PSD_YH(1) PSD_YH(2) PSD_YH(3) PSD_YH(4) PSD_YH(5) PSD_YH(6) PSD_YH(7)
                 PSD_YH(8) PSD_YH(9) PSD_YH(10) PSD_YH(11) PSD_YH(12) PSD_YH(13) PSD_YH(14) PSD_YH(15)
 #undef PSD_YH
             }
-            if (kHSV || kSUM) {
-                sad_h = __reduce_add_sync(0xFFFFFFFFu, sad_h);
-                sad_s = __reduce_add_sync(0xFFFFFFFFu, sad_s);
-                sad_v = __reduce_add_sync(0xFFFFFFFFu, sad_v);
-                bsum = __reduce_add_sync(0xFFFFFFFFu, bsum);
-                if (lane == 0) {
-                    if (kHSV) {
-                        atomicAdd(&sm.acc[stage][0], sad_h);
-                        atomicAdd(&sm.acc[stage][1], sad_s);
-                        atomicAdd(&sm.acc[stage][2], sad_v);
-                    }
-                    if (kSUM) atomicAdd(&sm.acc[stage][3], bsum);
-                }
-            }
         }
         __syncwarp();  // all lanes' shared atomics / ring reads precede the arrival
         if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (++stage == kWsStages) { stage = 0; parity ^= 1u; }
+    };
+
+    Px16 P0, P1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) P0.h[j] = P0.s[j] = P0.v[j] = P1.h[j] = P1.s[j] = P1.v[j] = 0;
+    int it = it_begin;
+#pragma unroll 1
+    for (; it + 1 < it_end; it += 2) {
+        step(it, P0, P1);
+        step(it + 1, P1, P0);
     }
+    if (it < it_end) step(it, P0, P1);
 }
 
 template <uint32_t F, int HV>
