@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps for the host-buffer e2e leg")
     ap.add_argument("--host-ring", type=int, default=256, help="distinct pinned host frames for e2e")
     ap.add_argument("--cpu-sample", type=int, default=400, help="frames in the cpu_baseline sample")
+    ap.add_argument("--edge-batch", type=int, default=128,
+                    help="frames per engine batch when the Canny/dilate edge component is on (its per-pixel "
+                         "scratch - V plane, class map, union-find labels - is 6 B/px per frame of a batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--detector", default="content", choices=["content", "content_edges", "threshold", "histogram"])
@@ -266,7 +269,7 @@ def run_ours(args):
     halo_t = torch.empty(fbytes, dtype=torch.uint8, device=f"cuda:{dev}") if world > 1 else None
     torch.cuda.synchronize()
 
-    max_batch = 2048 if not (features & 8) else 32
+    max_batch = 2048 if not (features & 8) else args.edge_batch
     sw, sh = W, H
     if args.auto_downscale:
         from pyscenedetect_b200.scene_manager import compute_downscale_factor

@@ -6,8 +6,12 @@
 // BORDER_REPLICATE, fixed-point non-maximum suppression (TG22 = 13573), double threshold with
 // strict '>' and 8-connected hysteresis.  oracle/intmath.py:canny is the CPU twin pinned
 // against cv2.Canny.  Stages: thresholds (from the V histogram the score pass produced) ->
-// gradient/NMS/classify -> hysteresis to a fix-point -> separable k x k max -> SAD against the
-// previous frame's dilated map.
+// gradient/NMS/classify -> hysteresis -> separable k x k max -> SAD against the previous frame's
+// dilated map.  Hysteresis ("weak pixels 8-connected to a strong pixel become edges") is solved as
+// connected-component labelling with a lock-free union-find over the weak+strong pixels: three
+// launches per batch whatever the length of the weak chains, no host round trip.  (The earlier
+// tile-local fix-point iteration needed ~100 chained launches per batch on noisy frames; it is kept
+// behind PSD_EDGE_HYSTERESIS=tiles as a cross-check.)
 #include "psd_common.cuh"
 
 namespace psd {
@@ -106,7 +110,223 @@ __global__ void __launch_bounds__(kClassifyThreads) psd_canny_classify_kernel(
     }
 }
 
-// ---- 3. hysteresis: tile-local fix-point, repeated until no tile changes ----
+// ---- 2b. the same classification, streamed through registers ----
+// One warp owns a band of kBandCols output columns x kBandRows rows and marches down it one image
+// row per step.  Lane l holds column (band start - 2 + l): a 2-column apron on each side covers the
+// Sobel and the non-maximum-suppression neighbourhoods, horizontal neighbours travel by warp shuffle,
+// vertical ones stay in registers (3 rows of V, 3 rows of magnitudes).  Per row: one byte load,
+// six shuffles, no shared memory, no barrier.  Same arithmetic as psd_canny_classify_kernel.
+constexpr int kBandCols = 28, kBandRows = 136;
+
+__global__ void __launch_bounds__(256) psd_canny_classify_stream_kernel(
+    const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint8_t* __restrict__ map, int W,
+    int H, int bands_x, int bands_y, int64_t n_warps) {
+    const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_warps) return;
+    const int lane = threadIdx.x & 31;
+    const int bx = (int)(wid % bands_x);
+    const int by = (int)((wid / bands_x) % bands_y);
+    const int64_t f = wid / ((int64_t)bands_x * bands_y);
+    const int64_t P = (int64_t)W * H;
+    const uint8_t* src = vplane + f * P;
+    uint8_t* dst = map + f * P;
+    const int low = thr[2 * f], high = thr[2 * f + 1];
+    const int xb = bx * kBandCols, yb = by * kBandRows;
+    const int ye = min(yb + kBandRows, H);
+    const int x = xb - 2 + lane;                 // this lane's column (may lie outside the image)
+    const int xc = min(max(x, 0), W - 1);        // BORDER_REPLICATE
+    const bool x_in = x >= 0 && x < W;
+    const bool writer = lane >= 2 && lane < 2 + kBandCols && x < W;
+    const unsigned full = 0xFFFFFFFFu;
+
+    int l0 = 0, l1 = 0;          // V of rows r-2, r-1
+    int rs0 = 0, rs1 = 0;        // horizontal 1-2-1 sums of rows r-2, r-1
+    int mU = 0, mUl = 0, mUr = 0;  // magnitudes of row r-3 (centre, left, right)
+    int mC = 0, mCl = 0, mCr = 0;  // ... row r-2
+    int gxC = 0, gyC = 0;          // gradient of row r-2
+    auto load_row = [&](int r) { return (int)src[(int64_t)min(max(r, 0), H - 1) * W + xc]; };
+    int l_next = load_row(yb - 2);
+    for (int r = yb - 2; r <= ye + 1; ++r) {
+        const int l2 = l_next;
+        l_next = load_row(r + 1);  // one row ahead of the shuffle chain (clamped: always in bounds)
+        const int rs2 = __shfl_up_sync(full, l2, 1) + 2 * l2 + __shfl_down_sync(full, l2, 1);
+        // gradient and magnitude of row r-1 (zero outside the image, as cv2 pads the magnitude buffer)
+        const int col = l0 + 2 * l1 + l2;
+        int gx = __shfl_down_sync(full, col, 1) - __shfl_up_sync(full, col, 1);
+        int gy = rs2 - rs0;
+        if (!(x_in && r - 1 >= 0 && r - 1 < H)) { gx = 0; gy = 0; }
+        const int mD = abs(gx) + abs(gy);
+        const int mDl = __shfl_up_sync(full, mD, 1), mDr = __shfl_down_sync(full, mD, 1);
+        // classify row r-2 from the magnitudes of rows r-3, r-2, r-1
+        const int y = r - 2;
+        if (y >= yb && y < ye && writer) {
+            const int m = mC;
+            uint8_t out = 0;
+            if (m > low) {
+                const int ax = abs(gxC);
+                const int ay = abs(gyC) << 15;
+                const int tg22x = ax * 13573;
+                const int tg67x = tg22x + (ax << 16);
+                bool keep;
+                if (ay < tg22x) {
+                    keep = (m > mCl) && (m >= mCr);
+                } else if (ay > tg67x) {
+                    keep = (m > mU) && (m >= mD);
+                } else if ((gxC ^ gyC) < 0) {  // s = -1: compare (y-1, x+1) and (y+1, x-1)
+                    keep = (m > mUr) && (m > mDl);
+                } else {                       // s = +1: compare (y-1, x-1) and (y+1, x+1)
+                    keep = (m > mUl) && (m > mDr);
+                }
+                if (keep) out = (m > high) ? 2 : 1;
+            }
+            dst[(int64_t)y * W + x] = out;
+        }
+        l0 = l1; l1 = l2;
+        rs0 = rs1; rs1 = rs2;
+        mU = mC; mUl = mCl; mUr = mCr;
+        mC = mD; mCl = mDl; mCr = mDr;
+        gxC = gx; gyC = gy;
+    }
+}
+
+// ---- 3a. hysteresis as connected components (union-find with atomicCAS, roots = smallest index) ----
+// labels[p] <= p always; a pixel is a root iff labels[p] == p.  Reads may see an older (larger)
+// ancestor, which is still an ancestor, so every race is benign; see ECL-CC (Jaiganesh & Burtscher).
+__device__ __forceinline__ int32_t ccl_find(int32_t* L, int32_t x) {
+    volatile int32_t* V = L;
+    int32_t y = V[x];
+    if (y != x) {
+        int32_t prev = x, next;
+        while (y > (next = V[y])) {  // intermediate pointer jumping
+            V[prev] = next;
+            prev = y;
+            y = next;
+        }
+    }
+    return y;
+}
+__device__ __forceinline__ void ccl_unite(int32_t* L, int32_t a, int32_t b) {
+    int32_t ra = ccl_find(L, a), rb = ccl_find(L, b);
+    while (ra != rb) {
+        if (ra < rb) { const int32_t t = ra; ra = rb; rb = t; }  // hang the larger root under the smaller
+        const int32_t old = atomicCAS(&L[ra], ra, rb);
+        if (old == ra) break;
+        ra = old;  // ra had stopped being a root: continue from its parent
+    }
+}
+
+// Initial labels: every edge pixel (class 1 or 2) points at the first pixel of its horizontal run, so
+// horizontal chains have depth 1 before any union.  One warp per image row walks it 32 pixels at a
+// time: the ballot of the edge flags gives the run start of every lane with two bit operations; a run
+// that touches the end of a 32-pixel chunk hands its start to the next chunk.
+__global__ void __launch_bounds__(256) psd_hyst_runs_kernel(const uint8_t* __restrict__ map,
+                                                            int32_t* __restrict__ labels, int W, int H,
+                                                            int64_t n_rows) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;  // frame * H + y
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int y = (int)(row % H);
+    const uint8_t* m = map + row * W;
+    int32_t* L = labels + row * W;
+    int carry = -1;  // x of the start of a run that reached the end of the previous chunk
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const bool e = x < W && m[x] != 0;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, e);
+        const uint32_t zeros_below = ~mask & ((2u << lane) - 1u);  // non-edge positions at or below this lane
+        int start;
+        if (zeros_below == 0u) start = carry >= 0 ? carry : x0;
+        else start = x0 + 32 - __clz(zeros_below);
+        if (e) L[x] = y * W + start;
+        const int s31 = __shfl_sync(0xFFFFFFFFu, start, 31);
+        carry = (mask >> 31) ? s31 : -1;
+    }
+}
+
+// Edge pixels are a few percent of a frame, so the three passes below scan the class map 16 bytes per
+// thread and only descend into non-zero bytes (a byte-per-thread grid spends its time launching CTAs).
+template <typename Fn>
+__device__ __forceinline__ void for_each_class_byte16(const uint8_t* map, int64_t total, Fn fn) {
+    const int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= total) return;
+    if (base + 16 <= total) {
+        const uint4 v = *reinterpret_cast<const uint4*>(map + base);
+        if ((v.x | v.y | v.z | v.w) == 0u) return;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (w[j] == 0u) continue;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t c = (w[j] >> (8 * b)) & 0xFFu;
+                if (c) fn(base + 4 * j + b, c);
+            }
+        }
+    } else {
+        for (int64_t g = base; g < total; ++g) {
+            const uint32_t c = map[g];
+            if (c) fn(g, c);
+        }
+    }
+}
+
+// Link the runs of adjacent rows (8-connectivity).  A run start looks at N, or at NW and NE when N is
+// not an edge pixel (N's run already contains NW and NE otherwise); a pixel inside a run only has to
+// add NE when N is not an edge pixel - every other contact was made by its W neighbour.
+// (tests/test_edge_ccl_model.py restates this rule on the CPU.)
+__global__ void __launch_bounds__(256) psd_hyst_union_kernel(const uint8_t* __restrict__ map,
+                                                             int32_t* __restrict__ labels, int W, int H,
+                                                             int64_t total) {
+    const int64_t P = (int64_t)W * H;
+    for_each_class_byte16(map, total, [&](int64_t g, uint32_t) {
+        const int64_t f = g / P;
+        const int32_t p = (int32_t)(g - f * P);
+        const int y = p / W, x = p - y * W;
+        if (y == 0) return;
+        const uint8_t* m = map + f * P;
+        int32_t* L = labels + f * P;
+        const bool w_edge = x > 0 && m[p - 1];
+        const bool n_edge = m[p - W] != 0;
+        const bool ne_edge = x + 1 < W && m[p - W + 1];
+        if (!w_edge) {
+            if (n_edge) {
+                ccl_unite(L, p, p - W);
+            } else {
+                if (x > 0 && m[p - W - 1]) ccl_unite(L, p, p - W - 1);
+                if (ne_edge) ccl_unite(L, p, p - W + 1);
+            }
+        } else if (!n_edge && ne_edge) {
+            ccl_unite(L, p, p - W + 1);
+        }
+    });
+}
+
+// strong pixels mark the root of their component as strong (the root is itself an edge pixel of
+// that component, so promoting it is part of the answer)
+__global__ void __launch_bounds__(256) psd_hyst_mark_kernel(uint8_t* map, int32_t* __restrict__ labels,
+                                                            int64_t P, int64_t total) {
+    for_each_class_byte16(map, total, [&](int64_t g, uint32_t c) {
+        if (c != 2u) return;
+        const int64_t f = g / P;
+        const int32_t p = (int32_t)(g - f * P);
+        const int32_t r = ccl_find(labels + f * P, p);
+        if (r != p) map[f * P + r] = 2;
+    });
+}
+
+// weak pixels whose root is strong become edges
+__global__ void __launch_bounds__(256) psd_hyst_resolve_kernel(uint8_t* map, int32_t* __restrict__ labels,
+                                                               int64_t P, int64_t total) {
+    for_each_class_byte16(map, total, [&](int64_t g, uint32_t c) {
+        if (c != 1u) return;
+        const int64_t f = g / P;
+        const int32_t p = (int32_t)(g - f * P);
+        const int32_t r = ccl_find(labels + f * P, p);
+        if (r != p && *(volatile uint8_t*)(map + f * P + r) == 2) map[g] = 2;
+    });
+}
+
+// ---- 3b. hysteresis, cross-check implementation: tile-local fix-point, repeated until no tile changes ----
 constexpr int HTX = 64, HTY = 32;  // tile size (pixels)
 
 // Launch i of a round reads flag[i-1] and returns at once when the previous launch changed
@@ -302,30 +522,60 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     psd_edge_thresholds_kernel<<<(n + 63) / 64, 64, 0, stream>>>(b.vhist, n, P, b.thresholds);
     PSD_CHECK_LAUNCH();
     dim3 cg((W + TX - 1) / TX, (H + TY - 1) / TY, (unsigned)n);
-    psd_canny_classify_kernel<<<cg, kClassifyThreads, 0, stream>>>(b.vplane, b.thresholds, b.map, W, H);
+    static const bool use_tiles = [] {
+        const char* v = getenv("PSD_EDGE_HYSTERESIS");
+        return v && v[0] == 't';
+    }();
+    static const bool classify_tiles = [] {
+        const char* v = getenv("PSD_EDGE_CLASSIFY");
+        return v && v[0] == 't';
+    }();
+    if (classify_tiles) {
+        psd_canny_classify_kernel<<<cg, kClassifyThreads, 0, stream>>>(b.vplane, b.thresholds, b.map, W, H);
+    } else {
+        const int bands_x = (W + kBandCols - 1) / kBandCols, bands_y = (H + kBandRows - 1) / kBandRows;
+        const int64_t n_warps = (int64_t)bands_x * bands_y * n;
+        psd_canny_classify_stream_kernel<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, stream>>>(
+            b.vplane, b.thresholds, b.map, W, H, bands_x, bands_y, n_warps);
+    }
     PSD_CHECK_LAUNCH();
     count_launch(2);
-    dim3 hg((W + HTX - 1) / HTX, (H + HTY - 1) / HTY, (unsigned)n);
-    // Each launch reaches a fix-point inside every tile; edges crossing tiles need another launch.
-    // A round enqueues kRound launches chained through device flags (a launch is a no-op once its
-    // predecessor changed nothing) and only then asks the host whether another round is needed.
-    constexpr int kRound = 8;
-    const size_t tiles = (size_t)hg.x * hg.y * n;
-    for (int round = 0; round < 100000; ++round) {
-        PSD_CUDA(cudaMemsetAsync(b.changed, 0, kRound * sizeof(int32_t), stream));
-        for (int rep = 0; rep < kRound; ++rep) {
-            const int launch = round * kRound + rep;
-            psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(
-                b.map, W, H, rep ? b.changed + rep - 1 : nullptr, b.changed + rep,
-                launch ? b.dirty + (size_t)((launch - 1) & 1) * tiles : nullptr,
-                b.dirty + (size_t)(launch & 1) * tiles);
-            PSD_CHECK_LAUNCH();
+    if (!use_tiles) {
+        const int64_t total = P * n;
+        const unsigned blocks = (unsigned)(((total + 15) / 16 + 255) / 256);
+        const int64_t n_rows = (int64_t)H * n;
+        psd_hyst_runs_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n_rows);
+        PSD_CHECK_LAUNCH();
+        psd_hyst_union_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, W, H, total);
+        PSD_CHECK_LAUNCH();
+        psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
+        PSD_CHECK_LAUNCH();
+        psd_hyst_resolve_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
+        PSD_CHECK_LAUNCH();
+        count_launch(4);
+    } else {
+        dim3 hg((W + HTX - 1) / HTX, (H + HTY - 1) / HTY, (unsigned)n);
+        // Each launch reaches a fix-point inside every tile; edges crossing tiles need another launch.
+        // A round enqueues kRound launches chained through device flags (a launch is a no-op once its
+        // predecessor changed nothing) and only then asks the host whether another round is needed.
+        constexpr int kRound = 8;
+        const size_t tiles = (size_t)hg.x * hg.y * n;
+        for (int round = 0; round < 100000; ++round) {
+            PSD_CUDA(cudaMemsetAsync(b.changed, 0, kRound * sizeof(int32_t), stream));
+            for (int rep = 0; rep < kRound; ++rep) {
+                const int launch = round * kRound + rep;
+                psd_hysteresis_kernel<<<hg, 256, 0, stream>>>(
+                    b.map, W, H, rep ? b.changed + rep - 1 : nullptr, b.changed + rep,
+                    launch ? b.dirty + (size_t)((launch - 1) & 1) * tiles : nullptr,
+                    b.dirty + (size_t)(launch & 1) * tiles);
+                PSD_CHECK_LAUNCH();
+            }
+            count_launch(kRound);
+            PSD_CUDA(cudaMemcpyAsync(b.changed_host, b.changed + kRound - 1, sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, stream));
+            PSD_CUDA(cudaStreamSynchronize(stream));
+            if (*b.changed_host == 0) break;
         }
-        count_launch(kRound);
-        PSD_CUDA(cudaMemcpyAsync(b.changed_host, b.changed + kRound - 1, sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, stream));
-        PSD_CUDA(cudaStreamSynchronize(stream));
-        if (*b.changed_host == 0) break;
     }
     const int r = ksize / 2;
     const int Wq = (W + 31) / 32;
