@@ -243,30 +243,21 @@ __global__ void __launch_bounds__(256) psd_hyst_runs_kernel(const uint8_t* __res
     }
 }
 
-// Edge pixels are a few percent of a frame, so the three passes below scan the class map 16 bytes per
-// thread and only descend into non-zero bytes (a byte-per-thread grid spends its time launching CTAs).
+// Edge pixels are a few percent of a frame and come in lines.  The three passes below give every
+// thread kScanPerThread pixels spaced one CTA width apart: a byte-per-thread grid spends its time
+// launching CTAs, and 16 CONSECUTIVE pixels per thread serialise the pointer chasing of a whole edge
+// segment in one thread (measured 3x slower); strided pixels keep the loads coalesced and spread an
+// edge segment over the threads of a warp.
+constexpr int kScanPerThread = 16;
 template <typename Fn>
 __device__ __forceinline__ void for_each_class_byte16(const uint8_t* map, int64_t total, Fn fn) {
-    const int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 16;
-    if (base >= total) return;
-    if (base + 16 <= total) {
-        const uint4 v = *reinterpret_cast<const uint4*>(map + base);
-        if ((v.x | v.y | v.z | v.w) == 0u) return;
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (w[j] == 0u) continue;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t c = (w[j] >> (8 * b)) & 0xFFu;
-                if (c) fn(base + 4 * j + b, c);
-            }
-        }
-    } else {
-        for (int64_t g = base; g < total; ++g) {
-            const uint32_t c = map[g];
-            if (c) fn(g, c);
-        }
+    const int64_t base = (int64_t)blockIdx.x * (kScanPerThread * 256) + threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < kScanPerThread; ++k) {
+        const int64_t g = base + k * 256;
+        if (g >= total) return;
+        const uint32_t c = map[g];
+        if (c) fn(g, c);
     }
 }
 
@@ -324,6 +315,161 @@ __global__ void __launch_bounds__(256) psd_hyst_resolve_kernel(uint8_t* map, int
         const int32_t r = ccl_find(labels + f * P, p);
         if (r != p && *(volatile uint8_t*)(map + f * P + r) == 2) map[g] = 2;
     });
+}
+
+// ---- 3c. hysteresis, production path: tile-local components in shared memory, then border links ----
+// The global union-find above is latency-bound: components are a few hundred pixels, but a vertical
+// edge is a chain of runs, and every hop of find() through HBM/L2 costs ~1 us.  Here one CTA labels a
+// 64x32 tile entirely in shared memory (run starts from row bit masks, unions and finds at ~30 cycles
+// per hop), resolves "weak next to strong" inside the tile at once, and writes for every edge pixel the
+// global index of its tile-local root.  Only contacts ACROSS tile borders go through the global
+// union-find (three thin launches over border pixels), so global trees are as deep as a component
+// is wide in tiles.  psd_hyst_mark_kernel / psd_hyst_resolve_kernel then finish components that span
+// tiles.  (tests/test_edge_ccl_model.py restates the decomposition on the CPU.)
+constexpr int CTW = 64, CTH = 32;
+
+__device__ __forceinline__ int sm_find(int32_t* L, int x) {
+    volatile int32_t* V = L;
+    int y = V[x];
+    if (y != x) {
+        int prev = x, next;
+        while (y > (next = V[y])) {
+            V[prev] = next;
+            prev = y;
+            y = next;
+        }
+    }
+    return y;
+}
+__device__ __forceinline__ void sm_unite(int32_t* L, int a, int b) {
+    int ra = sm_find(L, a), rb = sm_find(L, b);
+    while (ra != rb) {
+        if (ra < rb) { const int t = ra; ra = rb; rb = t; }
+        const int old = atomicCAS(&L[ra], ra, rb);
+        if (old == ra) break;
+        ra = old;
+    }
+}
+
+__global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict__ map,
+                                                            int32_t* __restrict__ labels, int W, int H) {
+    __shared__ uint8_t cls[CTH][CTW];
+    __shared__ int32_t lab[CTH * CTW];
+    __shared__ uint32_t rowmask[CTH][2];
+    __shared__ uint8_t strong_root[CTH * CTW];
+    __shared__ int any_edge;
+    const int tid = threadIdx.x;
+    const int row = tid >> 3, c0 = (tid & 7) * 8;  // 8 consecutive pixels of one tile row per thread
+    const int x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
+    const int64_t P = (int64_t)W * H;
+    uint8_t* m = map + (int64_t)blockIdx.z * P;
+    int32_t* Lg = labels + (int64_t)blockIdx.z * P;
+    if (tid < 2 * CTH) (&rowmask[0][0])[tid] = 0;
+    if (tid == 0) any_edge = 0;
+    __syncthreads();
+    const int gy = y0 + row;
+    uint32_t c[8];
+    uint32_t mask8 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gx = x0 + c0 + i;
+        c[i] = (gy < H && gx < W) ? m[(int64_t)gy * W + gx] : 0u;
+        cls[row][c0 + i] = (uint8_t)c[i];
+        strong_root[row * CTW + c0 + i] = 0;
+        if (c[i]) mask8 |= 1u << i;
+    }
+    if (mask8) {
+        atomicOr(&rowmask[row][c0 >> 5], mask8 << (c0 & 31));
+        any_edge = 1;
+    }
+    __syncthreads();
+    if (!any_edge) return;
+    // run starts: label = first pixel of the horizontal run inside this tile row
+    const unsigned long long m64 = (unsigned long long)rowmask[row][0] | ((unsigned long long)rowmask[row][1] << 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (!c[i]) continue;
+        const int col = c0 + i;
+        const unsigned long long zb = ~m64 & ((2ull << col) - 1ull);  // non-edge columns at or left of col
+        const int start = zb ? 64 - __clzll((long long)zb) : 0;
+        lab[row * CTW + col] = row * CTW + start;
+    }
+    __syncthreads();
+    // link the runs of adjacent tile rows (same rule as psd_hyst_union_kernel; outside the tile = no edge)
+    if (row > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!c[i]) continue;
+            const int col = c0 + i, p = row * CTW + col;
+            const bool w_edge = col > 0 && cls[row][col - 1];
+            const bool n_edge = cls[row - 1][col] != 0;
+            const bool ne_edge = col + 1 < CTW && cls[row - 1][col + 1];
+            if (!w_edge) {
+                if (n_edge) {
+                    sm_unite(lab, p, p - CTW);
+                } else {
+                    if (col > 0 && cls[row - 1][col - 1]) sm_unite(lab, p, p - CTW - 1);
+                    if (ne_edge) sm_unite(lab, p, p - CTW + 1);
+                }
+            } else if (!n_edge && ne_edge) {
+                sm_unite(lab, p, p - CTW + 1);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (c[i] == 2u) strong_root[sm_find(lab, row * CTW + c0 + i)] = 1;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (!c[i]) continue;
+        const int r = sm_find(lab, row * CTW + c0 + i);
+        const int64_t g = (int64_t)gy * W + x0 + c0 + i;
+        Lg[g] = (y0 + (r >> 6)) * W + x0 + (r & 63);  // global index of the tile-local root
+        if (c[i] == 1u && strong_root[r]) m[g] = 2;   // resolved inside the tile
+    }
+}
+
+// contacts across tile borders.  mode 0: pixels of the first row of a tile row (N, NW, NE lie in other
+// tiles); mode 1: first column of a tile column (W, NW); mode 2: last column of a tile column (NE).
+__global__ void __launch_bounds__(256) psd_hyst_border_kernel(const uint8_t* __restrict__ map,
+                                                              int32_t* __restrict__ labels, int W, int H,
+                                                              int n, int mode) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t P = (int64_t)W * H;
+    int x, y;
+    int64_t f;
+    if (mode == 0) {
+        const int lines = (H - 1) / CTH;  // tile rows 1..lines start at y = CTH * k
+        if (lines <= 0 || t >= (int64_t)n * lines * W) return;
+        x = (int)(t % W);
+        const int64_t q = t / W;
+        y = ((int)(q % lines) + 1) * CTH;
+        f = q / lines;
+    } else {
+        const int lines = (mode == 1) ? (W - 1) / CTW : (W - 1) / CTW;  // borders between tile columns
+        if (lines <= 0 || t >= (int64_t)n * lines * H) return;
+        y = (int)(t % H);
+        const int64_t q = t / H;
+        const int k = (int)(q % lines) + 1;
+        x = (mode == 1) ? k * CTW : k * CTW - 1;
+        f = q / lines;
+    }
+    const uint8_t* m = map + f * P;
+    int32_t* L = labels + f * P;
+    const int32_t p = y * W + x;
+    if (m[p] == 0) return;
+    if (mode == 0) {
+        if (m[p - W]) ccl_unite(L, p, p - W);
+        if (x > 0 && m[p - W - 1]) ccl_unite(L, p, p - W - 1);
+        if (x + 1 < W && m[p - W + 1]) ccl_unite(L, p, p - W + 1);
+    } else if (mode == 1) {
+        if (m[p - 1]) ccl_unite(L, p, p - 1);
+        if (y > 0 && m[p - W - 1]) ccl_unite(L, p, p - W - 1);
+    } else {
+        if (y > 0 && x + 1 < W && m[p - W + 1]) ccl_unite(L, p, p - W + 1);
+    }
 }
 
 // ---- 3b. hysteresis, cross-check implementation: tile-local fix-point, repeated until no tile changes ----
@@ -542,12 +688,30 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     count_launch(2);
     if (!use_tiles) {
         const int64_t total = P * n;
-        const unsigned blocks = (unsigned)(((total + 15) / 16 + 255) / 256);
-        const int64_t n_rows = (int64_t)H * n;
-        psd_hyst_runs_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n_rows);
-        PSD_CHECK_LAUNCH();
-        psd_hyst_union_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, W, H, total);
-        PSD_CHECK_LAUNCH();
+        const unsigned blocks = (unsigned)((total + kScanPerThread * 256 - 1) / (kScanPerThread * 256));
+        static const bool global_only = [] {
+            const char* v = getenv("PSD_EDGE_HYSTERESIS");
+            return v && v[0] == 'g';
+        }();
+        if (global_only) {  // cross-check: run labels + unions straight in global memory
+            const int64_t n_rows = (int64_t)H * n;
+            psd_hyst_runs_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n_rows);
+            PSD_CHECK_LAUNCH();
+            psd_hyst_union_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, W, H, total);
+            PSD_CHECK_LAUNCH();
+        } else {
+            dim3 tg((W + CTW - 1) / CTW, (H + CTH - 1) / CTH, (unsigned)n);
+            psd_hyst_tile_kernel<<<tg, 256, 0, stream>>>(b.map, b.labels, W, H);
+            PSD_CHECK_LAUNCH();
+            const int64_t hb = (int64_t)n * ((H - 1) / CTH) * W, vb = (int64_t)n * ((W - 1) / CTW) * H;
+            if (hb > 0) psd_hyst_border_kernel<<<(unsigned)((hb + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n, 0);
+            if (vb > 0) {
+                psd_hyst_border_kernel<<<(unsigned)((vb + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n, 1);
+                psd_hyst_border_kernel<<<(unsigned)((vb + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n, 2);
+            }
+            PSD_CHECK_LAUNCH();
+            count_launch(2);
+        }
         psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
         PSD_CHECK_LAUNCH();
         psd_hyst_resolve_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
