@@ -246,20 +246,24 @@ def test_device_resize_bit_exact(lib, src, dst):
     eng.close()
 
 
-def test_edge_intermediates_match_cv2(lib):
-    """V plane, Canny map and dilated edges of every frame vs cv2 (content_detector.py:213-239)."""
+@pytest.mark.parametrize("shape", [(320, 180), (131, 97), (70, 33), (29, 300)])
+def test_edge_intermediates_match_cv2(lib, shape):
+    """V plane, Canny map and dilated edges of every frame vs cv2 (content_detector.py:213-239).
+    The odd sizes exercise partial 64x32 hysteresis tiles, partial 28-column classify bands, rows
+    that are not a multiple of 4 bytes and images narrower than one tile."""
     from pyscenedetect_b200.engine import F_EDGES, Engine
     from pyscenedetect_b200.synth import ScenePlan, render_frames
-    frames = render_frames(ScenePlan(12, seed=4, min_len=4, max_len=8).params, 320, 180)
+    w, h = shape
+    frames = render_frames(ScenePlan(12, seed=4, min_len=4, max_len=8).params, w, h)
     rng = np.random.default_rng(0)
-    extra = np.stack([np.zeros((180, 320, 3), np.uint8), np.full((180, 320, 3), 255, np.uint8),
-                      rng.integers(0, 256, (180, 320, 3), dtype=np.uint8),
-                      cv2.GaussianBlur(rng.integers(0, 256, (180, 320, 3), dtype=np.uint8), (9, 9), 0)])
+    extra = np.stack([np.zeros((h, w, 3), np.uint8), np.full((h, w, 3), 255, np.uint8),
+                      rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
+                      cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (9, 9), 0)])
     frames = np.concatenate([frames, extra])
-    eng = Engine(320, 180, F_EDGES, max_batch=16)
+    eng = Engine(w, h, F_EDGES, max_batch=16)
     eng.submit(frames)
     k = eng.edge_kernel_size
-    assert k == R.estimated_kernel_size(320, 180)
+    assert k == R.estimated_kernel_size(w, h)
     kernel = np.ones((k, k), np.uint8)
     prev = None
     sums = eng.read_sums()
