@@ -353,10 +353,10 @@ __device__ __forceinline__ void sm_unite(int32_t* L, int a, int b) {
 
 __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict__ map,
                                                             int32_t* __restrict__ labels, int W, int H) {
-    __shared__ uint8_t cls[CTH][CTW];
+    __shared__ __align__(8) uint8_t cls[CTH][CTW];
     __shared__ int32_t lab[CTH * CTW];
     __shared__ uint32_t rowmask[CTH][2];
-    __shared__ uint8_t strong_root[CTH * CTW];
+    __shared__ __align__(8) uint8_t strong_root[CTH * CTW];
     __shared__ int any_edge;
     const int tid = threadIdx.x;
     const int row = tid >> 3, c0 = (tid & 7) * 8;  // 8 consecutive pixels of one tile row per thread
@@ -368,15 +368,27 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
     if (tid == 0) any_edge = 0;
     __syncthreads();
     const int gy = y0 + row;
-    uint32_t c[8];
-    uint32_t mask8 = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int gx = x0 + c0 + i;
-        c[i] = (gy < H && gx < W) ? m[(int64_t)gy * W + gx] : 0u;
-        cls[row][c0 + i] = (uint8_t)c[i];
-        strong_root[row * CTW + c0 + i] = 0;
-        if (c[i]) mask8 |= 1u << i;
+    // the thread's 8 class bytes travel as one 64-bit word; all loops below walk only its non-zero
+    // bytes (edge pixels are ~3 % of a frame), which also keeps the kernel small enough for the
+    // instruction cache - the fully unrolled first version spent most of its time in fetch stalls
+    unsigned long long cpack = 0;
+    if (gy < H) {
+        const int64_t g0 = (int64_t)gy * W + x0 + c0;
+        if ((W & 7) == 0 && x0 + c0 + 8 <= W) {
+            cpack = *reinterpret_cast<const unsigned long long*>(m + g0);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i)
+                if (x0 + c0 + i < W) cpack |= (unsigned long long)m[g0 + i] << (8 * i);
+        }
+    }
+    *reinterpret_cast<unsigned long long*>(&cls[row][c0]) = cpack;
+    *reinterpret_cast<unsigned long long*>(&strong_root[row * CTW + c0]) = 0ull;
+    uint32_t mask8 = 0;  // bit i set <=> pixel i of this thread is an edge pixel (class 1 or 2)
+    {
+        // a byte is non-zero <=> (b | b>>1) & 1 here, classes being 0, 1, 2
+        const unsigned long long nz = (cpack | (cpack >> 1)) & 0x0101010101010101ull;
+        mask8 = (uint32_t)((nz * 0x0102040810204080ull) >> 56);  // gather the eight flags into one byte
     }
     if (mask8) {
         atomicOr(&rowmask[row][c0 >> 5], mask8 << (c0 & 31));
@@ -384,12 +396,12 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
     }
     __syncthreads();
     if (!any_edge) return;
+    auto cls_of = [&](int i) { return (uint32_t)(cpack >> (8 * i)) & 0xFFu; };
     // run starts: label = first pixel of the horizontal run inside this tile row
     const unsigned long long m64 = (unsigned long long)rowmask[row][0] | ((unsigned long long)rowmask[row][1] << 32);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (!c[i]) continue;
-        const int col = c0 + i;
+#pragma unroll 1
+    for (uint32_t mm = mask8; mm; mm &= mm - 1) {
+        const int col = c0 + __ffs(mm) - 1;
         const unsigned long long zb = ~m64 & ((2ull << col) - 1ull);  // non-edge columns at or left of col
         const int start = zb ? 64 - __clzll((long long)zb) : 0;
         lab[row * CTW + col] = row * CTW + start;
@@ -397,10 +409,9 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
     __syncthreads();
     // link the runs of adjacent tile rows (same rule as psd_hyst_union_kernel; outside the tile = no edge)
     if (row > 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (!c[i]) continue;
-            const int col = c0 + i, p = row * CTW + col;
+#pragma unroll 1
+        for (uint32_t mm = mask8; mm; mm &= mm - 1) {
+            const int col = c0 + __ffs(mm) - 1, p = row * CTW + col;
             const bool w_edge = col > 0 && cls[row][col - 1];
             const bool n_edge = cls[row - 1][col] != 0;
             const bool ne_edge = col + 1 < CTW && cls[row - 1][col + 1];
@@ -417,17 +428,19 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (c[i] == 2u) strong_root[sm_find(lab, row * CTW + c0 + i)] = 1;
+#pragma unroll 1
+    for (uint32_t mm = mask8; mm; mm &= mm - 1) {
+        const int i = __ffs(mm) - 1;
+        if (cls_of(i) == 2u) strong_root[sm_find(lab, row * CTW + c0 + i)] = 1;
+    }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (!c[i]) continue;
+#pragma unroll 1
+    for (uint32_t mm = mask8; mm; mm &= mm - 1) {
+        const int i = __ffs(mm) - 1;
         const int r = sm_find(lab, row * CTW + c0 + i);
         const int64_t g = (int64_t)gy * W + x0 + c0 + i;
-        Lg[g] = (y0 + (r >> 6)) * W + x0 + (r & 63);  // global index of the tile-local root
-        if (c[i] == 1u && strong_root[r]) m[g] = 2;   // resolved inside the tile
+        Lg[g] = (y0 + (r >> 6)) * W + x0 + (r & 63);      // global index of the tile-local root
+        if (cls_of(i) == 1u && strong_root[r]) m[g] = 2;  // resolved inside the tile
     }
 }
 
@@ -591,7 +604,8 @@ __global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __res
 // rows: out = OR over |dx| <= r of the row shifted by dx (funnel shifts across word boundaries)
 __global__ void __launch_bounds__(256) psd_edge_dilate_rows_bits_kernel(const uint32_t* __restrict__ in,
                                                                         uint32_t* __restrict__ out,
-                                                                        int64_t n_words, int Wq, int r) {
+                                                                        int64_t n_words, int Wq, int r,
+                                                                        uint32_t last_word_mask) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_words) return;
     const int wq = (int)(i % Wq);
@@ -603,6 +617,9 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_rows_bits_kernel(const ui
         o |= __funnelshift_r(cur, nxt, s);  // pixel x+s -> bit position of x
         o |= __funnelshift_l(prv, cur, s);  // pixel x-s
     }
+    // columns >= W of the last word must stay 0: the SAD counts whole words (found by the 131x97 case
+    // of test_edge_intermediates_match_cv2: dilation spilled into the padding bits)
+    if (wq == Wq - 1) o &= last_word_mask;
     out[i] = o;
 }
 
@@ -749,7 +766,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     psd_edge_pack_kernel<<<kg, 256, 0, stream>>>(b.map, b.bits_in, W, H, Wq);
     PSD_CHECK_LAUNCH();
     psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
-        b.bits_in, b.bits_row, per_frame * n, Wq, r);
+        b.bits_in, b.bits_row, per_frame * n, Wq, r, (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu);
     PSD_CHECK_LAUNCH();
     dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
     psd_edge_dilate_cols_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_row, b.bits_dil, H, Wq, r);
