@@ -292,28 +292,30 @@ __global__ void __launch_bounds__(256) psd_hyst_union_kernel(const uint8_t* __re
     });
 }
 
-// strong pixels mark the root of their component as strong (the root is itself an edge pixel of
-// that component, so promoting it is part of the answer)
+// Strong pixels mark the root of their component as strong (the root is itself an edge pixel of that
+// component, so promoting it is part of the answer).  `sc` is the class that carries the mark: 2 when
+// the labels come straight from the global union-find, 3 ("strong tile-local root") after
+// psd_hyst_tile_kernel - then only one pixel per tile-local component has to chase its global root.
 __global__ void __launch_bounds__(256) psd_hyst_mark_kernel(uint8_t* map, int32_t* __restrict__ labels,
-                                                            int64_t P, int64_t total) {
+                                                            int64_t P, int64_t total, uint32_t sc) {
     for_each_class_byte16(map, total, [&](int64_t g, uint32_t c) {
-        if (c != 2u) return;
+        if (c != sc) return;
         const int64_t f = g / P;
         const int32_t p = (int32_t)(g - f * P);
         const int32_t r = ccl_find(labels + f * P, p);
-        if (r != p) map[f * P + r] = 2;
+        if (r != p) map[f * P + r] = (uint8_t)sc;
     });
 }
 
-// weak pixels whose root is strong become edges
+// weak pixels whose root carries the mark become edges
 __global__ void __launch_bounds__(256) psd_hyst_resolve_kernel(uint8_t* map, int32_t* __restrict__ labels,
-                                                               int64_t P, int64_t total) {
+                                                               int64_t P, int64_t total, uint32_t sc) {
     for_each_class_byte16(map, total, [&](int64_t g, uint32_t c) {
         if (c != 1u) return;
         const int64_t f = g / P;
         const int32_t p = (int32_t)(g - f * P);
         const int32_t r = ccl_find(labels + f * P, p);
-        if (r != p && *(volatile uint8_t*)(map + f * P + r) == 2) map[g] = 2;
+        if (r != p && *(volatile uint8_t*)(map + f * P + r) == sc) map[g] = 2;
     });
 }
 
@@ -440,7 +442,11 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
         const int r = sm_find(lab, row * CTW + c0 + i);
         const int64_t g = (int64_t)gy * W + x0 + c0 + i;
         Lg[g] = (y0 + (r >> 6)) * W + x0 + (r & 63);      // global index of the tile-local root
-        if (cls_of(i) == 1u && strong_root[r]) m[g] = 2;  // resolved inside the tile
+        // resolved inside the tile: members of a component with a strong pixel become 2, its root 3
+        if (strong_root[r]) {
+            const uint32_t nc = (r == row * CTW + c0 + i) ? 3u : 2u;
+            if (cls_of(i) != nc) m[g] = (uint8_t)nc;
+        }
     }
 }
 
@@ -579,7 +585,7 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
 }
 
 // ---- 4. dilate on bit-packed edge maps (32 pixels per word) ----
-// pack: bit i of word (y, wq) = (map[y][32*wq + i] == 2); pixels beyond W are 0
+// pack: bit i of word (y, wq) = (map[y][32*wq + i] >= 2, i.e. edge or marked root); pixels beyond W are 0
 __global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __restrict__ map,
                                                             uint32_t* __restrict__ bits, int W, int H,
                                                             int Wq) {
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __res
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
         const int x = (wq0 + j) * 32 + lane;
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, x < W && row[x] == 2);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, x < W && row[x] >= 2);
         if (lane == j) mine = b;
     }
     if (wq0 + lane < Wq) bits[(f * H + y) * Wq + wq0 + lane] = mine;
@@ -729,9 +735,10 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
             PSD_CHECK_LAUNCH();
             count_launch(2);
         }
-        psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
+        const uint32_t sc = global_only ? 2u : 3u;
+        psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total, sc);
         PSD_CHECK_LAUNCH();
-        psd_hyst_resolve_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total);
+        psd_hyst_resolve_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total, sc);
         PSD_CHECK_LAUNCH();
         count_launch(4);
     } else {

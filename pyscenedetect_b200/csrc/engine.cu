@@ -565,7 +565,7 @@ int psd_engine_timing_ms(psd_engine* e, float* total_ms, float* score_ms, uint64
 
 __global__ void psd_map_to_255_kernel(const uint8_t* in, uint8_t* out, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (in[i] == 2) ? 255 : 0;
+    if (i < n) out[i] = (in[i] >= 2) ? 255 : 0;  // 2 = edge, 3 = edge that is a marked component root
 }
 
 int psd_engine_debug_plane(psd_engine* e, int which, int64_t index, uint8_t* out, size_t cap) {

@@ -82,7 +82,7 @@ struct EdgeBuffers {
     uint8_t* vplane;    // [n][P] V of HSV (written by the score pass)
     uint32_t* vhist;    // [n][256]
     int32_t* thresholds;// [n][2] low, high
-    uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis 2 = edge
+    uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis >= 2 = edge
     int32_t* labels;    // [n][P] union-find parents of the edge pixels (hysteresis)
     uint8_t* tmp;       // [P] scratch for debug taps
     uint32_t* bits_in;  // [n][H][Wq] edge pixels, 32 per word
