@@ -393,11 +393,11 @@ def run_ours(args):
                 "algorithmic_bytes_per_frame": fbytes,
                 "launches": int(score_launches), "avg_launch_ms": score_ms_total / max(1, score_launches),
                 # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to the
-                # average launch of this run (profiles/r01n_ncu_score_ws_kernel_v7.txt: 6 469 776 120 B
+                # average launch of this run (profiles/r01z_ncu_score_ws_kernel_final.txt: 6 470 488 272 B
                 # for a 1024-frame 1080p launch = 1.016x the algorithmic bytes)
-                "traffic": ((6469776120.0 / 1024.0) * (N * args.steps / max(1, score_launches)) / 1e9
+                "traffic": ((6470488272.0 / 1024.0) * (N * args.steps / max(1, score_launches)) / 1e9
                             if (args.detector == "content" and (W, H) == (1920, 1080) and (sw, sh) == (W, H)) else None),
-                "traffic_unit": "GB per launch (ncu dram bytes, profiles/r01n_ncu_score_ws_kernel_v7.txt)",
+                "traffic_unit": "GB per launch (ncu dram bytes, profiles/r01z_ncu_score_ws_kernel_final.txt)",
                 "achieved_bytes_per_launch_gb": fbytes * N * args.steps / max(1, score_launches) / 1e9,
             },
         }
