@@ -307,18 +307,6 @@ __global__ void __launch_bounds__(256) psd_hyst_mark_kernel(uint8_t* map, int32_
     });
 }
 
-// weak pixels whose root carries the mark become edges
-__global__ void __launch_bounds__(256) psd_hyst_resolve_kernel(uint8_t* map, int32_t* __restrict__ labels,
-                                                               int64_t P, int64_t total, uint32_t sc) {
-    for_each_class_byte16(map, total, [&](int64_t g, uint32_t c) {
-        if (c != 1u) return;
-        const int64_t f = g / P;
-        const int32_t p = (int32_t)(g - f * P);
-        const int32_t r = ccl_find(labels + f * P, p);
-        if (r != p && *(volatile uint8_t*)(map + f * P + r) == sc) map[g] = 2;
-    });
-}
-
 // ---- 3c. hysteresis, production path: tile-local components in shared memory, then border links ----
 // The global union-find above is latency-bound: components are a few hundred pixels, but a vertical
 // edge is a chain of runs, and every hop of find() through HBM/L2 costs ~1 us.  Here one CTA labels a
@@ -353,21 +341,28 @@ __device__ __forceinline__ void sm_unite(int32_t* L, int a, int b) {
     }
 }
 
+// rec: 16 words per tile - [0] = number of strong tile-local roots, [1..15] = their in-frame pixel index
+// (more than 15: the mark pass scans the tile instead)
+constexpr int kTileRec = 16;
 __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict__ map,
-                                                            int32_t* __restrict__ labels, int W, int H) {
+                                                            int32_t* __restrict__ labels,
+                                                            int32_t* __restrict__ tile_rec, int W, int H) {
     __shared__ __align__(8) uint8_t cls[CTH][CTW];
     __shared__ int32_t lab[CTH * CTW];
     __shared__ uint32_t rowmask[CTH][2];
     __shared__ __align__(8) uint8_t strong_root[CTH * CTW];
     __shared__ int any_edge;
+    __shared__ int n_sroots;
+    __shared__ int32_t sroots[kTileRec - 1];
     const int tid = threadIdx.x;
     const int row = tid >> 3, c0 = (tid & 7) * 8;  // 8 consecutive pixels of one tile row per thread
     const int x0 = blockIdx.x * CTW, y0 = blockIdx.y * CTH;
     const int64_t P = (int64_t)W * H;
     uint8_t* m = map + (int64_t)blockIdx.z * P;
     int32_t* Lg = labels + (int64_t)blockIdx.z * P;
+    int32_t* rec = tile_rec + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kTileRec;
     if (tid < 2 * CTH) (&rowmask[0][0])[tid] = 0;
-    if (tid == 0) any_edge = 0;
+    if (tid == 0) { any_edge = 0; n_sroots = 0; }
     __syncthreads();
     const int gy = y0 + row;
     // the thread's 8 class bytes travel as one 64-bit word; all loops below walk only its non-zero
@@ -397,7 +392,10 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
         any_edge = 1;
     }
     __syncthreads();
-    if (!any_edge) return;
+    if (!any_edge) {
+        if (tid == 0) rec[0] = 0;
+        return;
+    }
     auto cls_of = [&](int i) { return (uint32_t)(cpack >> (8 * i)) & 0xFFu; };
     // run starts: label = first pixel of the horizontal run inside this tile row
     const unsigned long long m64 = (unsigned long long)rowmask[row][0] | ((unsigned long long)rowmask[row][1] << 32);
@@ -444,9 +442,49 @@ __global__ void __launch_bounds__(256) psd_hyst_tile_kernel(uint8_t* __restrict_
         Lg[g] = (y0 + (r >> 6)) * W + x0 + (r & 63);      // global index of the tile-local root
         // resolved inside the tile: members of a component with a strong pixel become 2, its root 3
         if (strong_root[r]) {
-            const uint32_t nc = (r == row * CTW + c0 + i) ? 3u : 2u;
+            const bool is_root = (r == row * CTW + c0 + i);
+            const uint32_t nc = is_root ? 3u : 2u;
             if (cls_of(i) != nc) m[g] = (uint8_t)nc;
+            if (is_root) {
+                const int slot = atomicAdd(&n_sroots, 1);
+                if (slot < kTileRec - 1) sroots[slot] = (int32_t)g;
+            }
         }
+    }
+    __syncthreads();
+    if (tid == 0) rec[0] = n_sroots;
+    else if (tid < kTileRec && tid - 1 < n_sroots) rec[tid] = sroots[tid - 1];
+}
+
+// every strong tile-local root (class 3) marks its global root: one thread per tile record
+__global__ void __launch_bounds__(256) psd_hyst_mark_tiles_kernel(uint8_t* map, int32_t* __restrict__ labels,
+                                                                  const int32_t* __restrict__ tile_rec, int W,
+                                                                  int H, int tiles_x, int tiles_y, int64_t n_tiles) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int32_t* rec = tile_rec + t * kTileRec;
+    const int cnt = rec[0];
+    if (cnt == 0) return;
+    const int64_t P = (int64_t)W * H;
+    const int64_t f = t / ((int64_t)tiles_x * tiles_y);
+    uint8_t* m = map + f * P;
+    int32_t* L = labels + f * P;
+    if (cnt <= kTileRec - 1) {
+        for (int k = 0; k < cnt; ++k) {
+            const int32_t p = rec[1 + k];
+            const int32_t r = ccl_find(L, p);
+            if (r != p) m[r] = 3;
+        }
+    } else {  // more strong components in this tile than the record holds: look at every pixel of the tile
+        const int tt = (int)(t - f * tiles_x * tiles_y);
+        const int x0 = (tt % tiles_x) * CTW, y0 = (tt / tiles_x) * CTH;
+        for (int y = y0; y < min(y0 + CTH, H); ++y)
+            for (int x = x0; x < min(x0 + CTW, W); ++x) {
+                const int32_t p = y * W + x;
+                if (*(volatile uint8_t*)(m + p) != 3) continue;
+                const int32_t r = ccl_find(L, p);
+                if (r != p) m[r] = 3;
+            }
     }
 }
 
@@ -585,10 +623,12 @@ __global__ void __launch_bounds__(256) psd_hysteresis_kernel(uint8_t* __restrict
 }
 
 // ---- 4. dilate on bit-packed edge maps (32 pixels per word) ----
-// pack: bit i of word (y, wq) = (map[y][32*wq + i] >= 2, i.e. edge or marked root); pixels beyond W are 0
-__global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __restrict__ map,
-                                                            uint32_t* __restrict__ bits, int W, int H,
-                                                            int Wq) {
+// pack: bit i of word (y, wq) = pixel (y, 32*wq + i) is an edge; pixels beyond W are 0.  With sc != 0
+// the last step of the hysteresis is folded in: a weak pixel (class 1) whose component root carries the
+// mark `sc` is an edge too (and is written back as class 2 for the debug taps); classes >= 2 are edges.
+__global__ void __launch_bounds__(256) psd_edge_pack_kernel(uint8_t* map, int32_t* __restrict__ labels,
+                                                            uint32_t sc, uint32_t* __restrict__ bits, int W,
+                                                            int H, int Wq) {
     const int64_t P = (int64_t)W * H;
     const int64_t f = blockIdx.z;
     const int y = blockIdx.y;
@@ -596,12 +636,26 @@ __global__ void __launch_bounds__(256) psd_edge_pack_kernel(const uint8_t* __res
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp -> 32 words of this row
     const int wq0 = warp * 32;
     if (wq0 >= Wq) return;
-    const uint8_t* row = map + f * P + (int64_t)y * W;
+    uint8_t* mf = map + f * P;
+    int32_t* L = labels + f * P;
     uint32_t mine = 0;
-#pragma unroll 4
+#pragma unroll 1
     for (int j = 0; j < 32; ++j) {
         const int x = (wq0 + j) * 32 + lane;
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, x < W && row[x] >= 2);
+        bool edge = false;
+        if (x < W) {
+            const int32_t p = y * W + x;
+            const uint32_t c = mf[p];
+            edge = c >= 2u;
+            if (c == 1u && sc != 0u) {
+                const int32_t r = ccl_find(L, p);
+                if (r != p && *(volatile uint8_t*)(mf + r) == sc) {
+                    edge = true;
+                    mf[p] = 2;
+                }
+            }
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, edge);
         if (lane == j) mine = b;
     }
     if (wq0 + lane < Wq) bits[(f * H + y) * Wq + wq0 + lane] = mine;
@@ -709,6 +763,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     }
     PSD_CHECK_LAUNCH();
     count_launch(2);
+    uint32_t resolve_class = 0;  // class that marks a strong component root; 0 = the map is already final
     if (!use_tiles) {
         const int64_t total = P * n;
         const unsigned blocks = (unsigned)((total + kScanPerThread * 256 - 1) / (kScanPerThread * 256));
@@ -722,9 +777,12 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
             PSD_CHECK_LAUNCH();
             psd_hyst_union_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, W, H, total);
             PSD_CHECK_LAUNCH();
+            psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total, 2u);
+            PSD_CHECK_LAUNCH();
+            count_launch(3);
         } else {
             dim3 tg((W + CTW - 1) / CTW, (H + CTH - 1) / CTH, (unsigned)n);
-            psd_hyst_tile_kernel<<<tg, 256, 0, stream>>>(b.map, b.labels, W, H);
+            psd_hyst_tile_kernel<<<tg, 256, 0, stream>>>(b.map, b.labels, b.tile_rec, W, H);
             PSD_CHECK_LAUNCH();
             const int64_t hb = (int64_t)n * ((H - 1) / CTH) * W, vb = (int64_t)n * ((W - 1) / CTW) * H;
             if (hb > 0) psd_hyst_border_kernel<<<(unsigned)((hb + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n, 0);
@@ -733,14 +791,13 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
                 psd_hyst_border_kernel<<<(unsigned)((vb + 255) / 256), 256, 0, stream>>>(b.map, b.labels, W, H, n, 2);
             }
             PSD_CHECK_LAUNCH();
-            count_launch(2);
+            const int64_t n_tiles = (int64_t)tg.x * tg.y * n;
+            psd_hyst_mark_tiles_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(
+                b.map, b.labels, b.tile_rec, W, H, (int)tg.x, (int)tg.y, n_tiles);
+            PSD_CHECK_LAUNCH();
+            count_launch(5);
         }
-        const uint32_t sc = global_only ? 2u : 3u;
-        psd_hyst_mark_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total, sc);
-        PSD_CHECK_LAUNCH();
-        psd_hyst_resolve_kernel<<<blocks, 256, 0, stream>>>(b.map, b.labels, P, total, sc);
-        PSD_CHECK_LAUNCH();
-        count_launch(4);
+        resolve_class = global_only ? 2u : 3u;  // the resolve step itself is folded into psd_edge_pack_kernel
     } else {
         dim3 hg((W + HTX - 1) / HTX, (H + HTY - 1) / HTY, (unsigned)n);
         // Each launch reaches a fix-point inside every tile; edges crossing tiles need another launch.
@@ -770,7 +827,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     const int64_t per_frame = (int64_t)H * Wq;
     dim3 kg((unsigned)((Wq + 31) / 32 * 32 + 255) / 256, (unsigned)H, (unsigned)n);  // 8 warps per block
     kg.x = (unsigned)(((Wq + 31) / 32 + 7) / 8);
-    psd_edge_pack_kernel<<<kg, 256, 0, stream>>>(b.map, b.bits_in, W, H, Wq);
+    psd_edge_pack_kernel<<<kg, 256, 0, stream>>>(b.map, b.labels, resolve_class, b.bits_in, W, H, Wq);
     PSD_CHECK_LAUNCH();
     psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
         b.bits_in, b.bits_row, per_frame * n, Wq, r, (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu);

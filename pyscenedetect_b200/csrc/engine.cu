@@ -256,7 +256,7 @@ void psd_engine_destroy(psd_engine* e) {
     cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.map);
     cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
-    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed); cudaFree(e->eb.dirty); cudaFree(e->eb.labels);
+    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed); cudaFree(e->eb.dirty); cudaFree(e->eb.labels); cudaFree(e->eb.tile_rec);
     if (e->eb.changed_host) cudaFreeHost(e->eb.changed_host);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -345,6 +345,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         ENG_CUDA(cudaMalloc(&e->eb.vplane, plane));
         ENG_CUDA(cudaMalloc(&e->eb.map, plane));
         ENG_CUDA(cudaMalloc(&e->eb.labels, plane * sizeof(int32_t)));
+        ENG_CUDA(cudaMalloc(&e->eb.tile_rec, (size_t)e->max_batch * ((e->W + 63) / 64) * ((e->H + 31) / 32) * 16 * sizeof(int32_t)));
         const size_t words = (size_t)e->H * ((e->W + 31) / 32);
         ENG_CUDA(cudaMalloc(&e->eb.tmp, (size_t)e->P));
         ENG_CUDA(cudaMalloc(&e->eb.bits_in, words * 4 * e->max_batch));

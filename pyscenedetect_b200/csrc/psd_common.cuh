@@ -84,6 +84,7 @@ struct EdgeBuffers {
     int32_t* thresholds;// [n][2] low, high
     uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis >= 2 = edge
     int32_t* labels;    // [n][P] union-find parents of the edge pixels (hysteresis)
+    int32_t* tile_rec;  // [n][tiles][16] strong tile-local roots found by psd_hyst_tile_kernel
     uint8_t* tmp;       // [P] scratch for debug taps
     uint32_t* bits_in;  // [n][H][Wq] edge pixels, 32 per word
     uint32_t* bits_row; // [n][H][Wq] row-dilated

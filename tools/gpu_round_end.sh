@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end validation + evidence run (one gpurun call): GPU suite, smoke, every bench line, ncu captures
-O=gpurun_out/r01z; mkdir -p $O
+O=gpurun_out/round_end; mkdir -p $O
 timeout 900 python -m pytest tests -q -x -m gpu > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
 timeout 300 python __graft_entry__.py smoke > $O/smoke.txt 2>&1; tail -1 $O/smoke.txt
 timeout 600 python bench.py > $O/bench.json 2> $O/bench.err
