@@ -65,8 +65,9 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []   # (arrival time, csv line)
         self.thread = None
+        self.window: tuple[float, float] | None = None  # keep only samples that arrived inside it
 
     def start(self):
         try:
@@ -78,7 +79,7 @@ class ClockSampler:
             return
         def pump():
             for line in self.proc.stdout:
-                self.lines.append(line.strip())
+                self.lines.append((time.perf_counter(), line.strip()))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
@@ -90,23 +91,36 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(window):
+            sm, smax, power, reasons = [], [], [], set()
+            for stamp, line in self.lines:
+                # nvidia-smi needs ~0.1 s to start, so the sampler is started before the warm-up steps
+                # and the samples are cut to the timed region afterwards (25 ms period)
+                if window is not None and not (window[0] <= stamp <= window[1]):
+                    continue
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, power, reasons
+
+        sm, smax, power, reasons = collect(self.window)
+        scope = "timed region"
+        if not sm and self.window is not None:  # timed region shorter than one sample period
+            sm, smax, power, reasons = collect(None)
+            scope = "warm-up + timed region"
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
-                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": float(max(power)), "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -329,14 +343,14 @@ def run_ours(args):
         eng.sync()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_synced()
-    sampler = ClockSampler(dev)
     launches0 = lib.psd_launch_count()
     eng.timing_reset()
     barrier()
-    if rank == 0:
-        sampler.start()
     t0 = time.perf_counter()
     ev_begin, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_begin.record(ext_stream)  # CUDA events on the stream the kernels are launched on
@@ -353,6 +367,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     ev_ms_total = ev_begin.elapsed_time(ev_end)
+    sampler.window = (t0, t0 + wall)
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.psd_launch_count() - launches0
     # device time per step (CUDA events on the engine's compute stream) and wall time; max over ranks
