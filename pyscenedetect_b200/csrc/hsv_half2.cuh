@@ -12,13 +12,14 @@
 //     selects per pair;
 //   * only the two table products stay per pixel and in fp32: HADD2.F32 lifts a lane of d / h,
 //     yS = fma.rz(d, sdiv/4096, 32768.5), yH = fma.rm(h, hdiv/4096, 49152.5) exactly as in variant 4
-//     (byte 1 of the result = S resp. H mod 256), with the LUT row address of lane 0 built by one
-//     PRMT and of lane 1 by one IMAD.HI (x >> 8) - so the two 16-lane halves stay balanced;
+//     (byte 1 of the result = S resp. H mod 256), with each LUT row address built by one IDP2A
+//     (u16 lane x 128 + addend; PSD_V7_ADDR selects PRMT / IMAD.HI alternatives, measured equal);
 //   * "H += 180 if H < 0" is applied after packing, on four pixels at once: H mod 256 is either
 //     0..179 or 226..255, so a byte is negative iff its bits 7 and 6 are both set, and adding 180
 //     mod 256 equals subtracting 76 without a borrow.
 // Every step is an exact integer identity; pinned over all 2^24 colours by tests/test_gpu_parity.py
-// (psd_test_hsv, variant 7) and restated in numpy by tests/test_host_logic.py::test_variant7_model.
+// (psd_test_hsv, variants 7 and 8) and restated in numpy by tests/v7_model.py, which
+// tests/test_v7_model.py pins against the oracle over all 2^24 colours on the CPU.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -33,7 +34,8 @@ namespace psd {
 //   PSD_V7_ADDR 0: rows of 128 B in two tables (sdiv | hdiv); both lanes use IDP2A
 //                  (u16 lane x 128 + addend): fma half of the sub-partition
 //   PSD_V7_ADDR 1: rows of 256 B (sdiv column | hdiv column, the variant-4 layout); lane 0 uses PRMT
-//                  (alu half), lane 1 IMAD.HI (x >> 8, fma half)
+//                  (alu half), lane 1 IMAD.HI (x >> 8, fma half; needs shift24 == 0x01000000 at run time,
+//                  which only the engine passes - tools/microbench/hsv_rate.cu cannot run this mode)
 //   PSD_V7_ADDR 2: 256 B rows, both lanes PRMT
 #ifndef PSD_V7_ADDR
 #define PSD_V7_ADDR 0
