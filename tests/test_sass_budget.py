@@ -1,0 +1,62 @@
+"""Static checks on the compiled sm_100a code (no GPU needed): the fused pass really uses the
+instructions DESIGN.md says it does, nothing spills to local memory, and the two loops whose
+instruction count IS the performance (the kernel is issue-bound) stay within their budgets.  Runs on
+the in-tree libpsd_b200.so that __graft_entry__.build() produces; skipped without cuobjdump."""
+
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from pyscenedetect_b200 import _capi
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP) or not os.path.exists(_capi.LIB_PATH),
+                                reason="needs cuobjdump and the built library")
+
+WS_HSV_V7 = "_ZN3psd19psd_score_ws_kernelILj1ELi7EEEvNS_9ScoreArgsE"
+TILE_HYST = "_ZN3psd20psd_hyst_tile_kernelEPhPiS1_ii"
+LINE = re.compile(r"^\s+/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Za-z0-9_.]+)")
+
+
+def sass(function):
+    out = subprocess.run([CUOBJDUMP, "-sass", "-fun", function, _capi.LIB_PATH], capture_output=True, text=True,
+                         timeout=300).stdout
+    rows = [(int(m.group(1), 16), m.group(2), line) for line in out.splitlines() if (m := LINE.match(line))]
+    assert rows, f"{function} not found in {_capi.LIB_PATH}"
+    return rows
+
+
+def loops(rows):
+    """(start index, end index) of every backward branch"""
+    addr_to_idx = {a: i for i, (a, _, _) in enumerate(rows)}
+    res = []
+    for i, (a, op, line) in enumerate(rows):
+        m = re.search(r"BRA\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", line)
+        if op.startswith("BRA") and m and int(m.group(1), 16) < a and int(m.group(1), 16) in addr_to_idx:
+            res.append((addr_to_idx[int(m.group(1), 16)], i))
+    return res
+
+
+def test_ws_kernel_instruction_mix_and_budget():
+    rows = sass(WS_HSV_V7)
+    ops = [op for _, op, _ in rows]
+    for needed in ("UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "VIMNMX3.U16x2", "HFMA2", "HADD2.F32", "HSET2.EQ.AND",
+                   "IDP.2A.LO.U16.U8", "VABSDIFF4.U8.ACC", "FFMA.RZ", "FFMA.RM", "LDS.128", "ATOMS.ADD"):
+        assert any(o.startswith(needed) for o in ops), f"{needed} missing from the fused pass"
+    assert not any(o.startswith(("LDL", "STL")) for o in ops), "the fused pass spills to local memory"
+    # consumer loop = the innermost backward branch whose body holds the 2 x 3 LDS.128 of two frames
+    bodies = [rows[a:b + 1] for a, b in loops(rows)]
+    cons = min((b for b in bodies if sum(op == "LDS.128" for _, op, _ in b) == 6), key=len)
+    per_frame = len(cons) / 2
+    assert per_frame <= 370, f"consumer loop grew to {per_frame} instructions per frame (16 px per thread)"
+    # no warp reduction / election code on the consumer side any more
+    assert not any(op.startswith(("REDUX", "VOTEU", "UFLO")) for _, op, _ in cons)
+
+
+def test_tile_hysteresis_kernel_fits_the_instruction_cache():
+    rows = sass(TILE_HYST)
+    assert len(rows) <= 900, f"psd_hyst_tile_kernel is {len(rows)} instructions (the unrolled 3500 stalled on fetch)"
+    assert not any(op.startswith(("LDL", "STL")) for _, op, _ in rows)
