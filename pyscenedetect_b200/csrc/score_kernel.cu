@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 #define PSD_WS_WARPS 24
 #endif
 #ifndef PSD_WS_STAGES
-#define PSD_WS_STAGES 3
+#define PSD_WS_STAGES 4
 #endif
 constexpr int kWsConsumerWarps = PSD_WS_WARPS;
 constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
@@ -330,6 +330,7 @@ struct __align__(128) WsSmem {
     // flushes the difference, so its bookkeeping needs no ordering against the consumers' adds.
     uint32_t accl[kWsStages][4][32];
     uint32_t accl_seen[kWsStages][4][32];
+    uint32_t accl_sink[kWsStages][4][32];  // where threads without pixels / without a predecessor frame add
     uint32_t yhist[kWsStages][256];
     uint32_t vhist[kWsStages][256];
 };
@@ -360,6 +361,197 @@ __device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, uint32_t
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- consumer side, second form (PSD_WS_LOOP 1, the default) -------------------------------------
+// Same arithmetic as the first form; what changed is everything around it, because the pass is
+// issue-bound and ~10 % of the first loop's issue slots were bookkeeping:
+//   * the ring has 4 stages and the loop body covers PSD_WS_UNROLL (2 or 4) frames, so a frame's stage
+//     is a compile-time offset from one base register per body (ring, barrier, accumulator addresses
+//     are [reg + immediate] operands instead of IMAD/LEA/SEL chains per frame);
+//   * the SADs are always computed and only the three shared adds are predicated (no BSSY/BRA/BSYNC
+//     around them); the first frame of a chunk, which has no predecessor, just wastes 12 VABSDIFF4;
+//   * the wait parity flips once per ring revolution instead of a compare + select per frame.
+#ifndef PSD_WS_LOOP
+#define PSD_WS_LOOP 1
+#endif
+#ifndef PSD_WS_UNROLL
+#define PSD_WS_UNROLL 2
+#endif
+#ifndef PSD_WS_SYNCWARP
+// 0: no __syncwarp() in front of lane 0's EMPTY arrival.  The warp is converged there (every branch of the
+// step is closed by the compiler's BSSY/BSYNC pair), its lanes' LDS results were consumed by the arithmetic
+// above and its shared REDs entered the same in-order shared-memory pipe before the arrival does; the
+// convergence check costs UMOV + BRA.DIV + NOP + three register copies per frame.
+#define PSD_WS_SYNCWARP 0
+#endif
+#ifndef PSD_WS_STAGGER
+#define PSD_WS_STAGGER 0  // ns of start-up delay per warp slot of a sub-partition (de-phases its warps)
+#endif
+#if PSD_WS_LOOP
+static_assert(kWsStages % PSD_WS_UNROLL == 0, "the stage ring must be a whole number of loop bodies");
+#endif
+
+struct WsAddr {  // shared-window addresses of the current loop body's first stage
+    uint32_t ring;   // + tid * 48
+    uint32_t full;   // FULL mbarrier of the stage; EMPTY mbarriers follow kWsStages * 8 bytes later
+    uint32_t acc;    // per-lane accumulators of the stage (this lane's word of channel 0)
+};
+
+template <int OFF>
+__device__ __forceinline__ void mbar_wait_hint_off(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%3], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(20000u), "n"(OFF)
+        : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void lds128_off(uint32_t addr, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr), "n"(OFF));
+}
+template <int OFF>
+__device__ __forceinline__ void red_shared_add_off(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void mbar_arrive_off(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar), "n"(OFF) : "memory");
+}
+
+// One frame of the consumer loop at stage (body base + J).  `sad_acc`: accumulator base the SADs go to (the
+// stage's real per-lane words, or the sink); `mine`: the frame is not the halo and the thread owns pixels.
+template <uint32_t F, int HV, int J>
+__device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const WsAddr& ad, uint32_t parity, int stage0,
+                                        uint32_t sad_acc, bool mine, int fi, int my_px, int lane, uint32_t zero,
+                                        const LutView& lut, const LutView7& lut7, const Px16& prev, Px16& cur) {
+    constexpr bool kHSV = (F & PSD_F_HSV) != 0;
+    constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
+    constexpr bool kYH = (F & PSD_F_YHIST) != 0;
+    constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
+    mbar_wait_hint_off<J * 8>(ad.full, parity);
+    uint32_t w[12];
+    // idle threads of a partial last strip read stale ring bytes; they never contribute (add_sad / mine)
+    lds128_off<J * kWsStripBytes>(ad.ring, w[0], w[1], w[2], w[3]);
+    lds128_off<J * kWsStripBytes + 16>(ad.ring, w[4], w[5], w[6], w[7]);
+    lds128_off<J * kWsStripBytes + 32>(ad.ring, w[8], w[9], w[10], w[11]);
+    if (kHSV) {
+        if (HV >= 7) hsv16_v7<HV == 8>(w, cur, lut7, a.shift24);
+        else hsv16_v4(w, cur, lut);
+        // one dependent VABSDIFF4.ACC chain per plane (the compiler otherwise splits each into four
+        // zero-seeded accumulators plus an IADD3 tree: 12 extra issue slots per frame)
+        uint32_t sad_h = sad4_acc(cur.h[0], prev.h[0], zero), sad_s = sad4_acc(cur.s[0], prev.s[0], zero),
+                 sad_v = sad4_acc(cur.v[0], prev.v[0], zero);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            sad_h = sad4_acc(cur.h[j], prev.h[j], sad_h);
+            sad_s = sad4_acc(cur.s[j], prev.s[j], sad_s);
+            sad_v = sad4_acc(cur.v[j], prev.v[j], sad_v);
+        }
+        // never predicated: threads whose SADs do not count (no pixels, no predecessor frame) were handed the
+        // address of the sink accumulators instead
+        red_shared_add_off<J * 512>(sad_acc, sad_h);
+        red_shared_add_off<J * 512 + 128>(sad_acc, sad_s);
+        red_shared_add_off<J * 512 + 256>(sad_acc, sad_v);
+        if (kEDGE && mine) {
+            uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
+            if ((a.n_pixels & 15) == 0) {
+                *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
+            } else {
+                for (int p = 0; p < kPxPerThread; ++p) vp[p] = (uint8_t)(cur.v[p >> 2] >> ((p & 3) * 8));
+            }
+            uint32_t* vh = sm.vhist[stage0 + J];
+#pragma unroll
+            for (int p = 0; p < kPxPerThread; ++p) atomicAdd(&vh[(cur.v[p >> 2] >> ((p & 3) * 8)) & 0xFF], 1u);
+        }
+    }
+    if (mine) {
+        if (kSUM) {
+            uint32_t bsum = 0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
+            red_shared_add_off<J * 512 + 384>(ad.acc, bsum);
+        }
+        if (kYH) {
+            uint32_t* hist = sm.yhist[stage0 + J];
+#define PSD_YH(i) atomicAdd(&hist[y_of_pixel<i>(w)], 1u);
+            PSD_YH(0) PSD_YH(1) PSD_YH(2) PSD_YH(3) PSD_YH(4) PSD_YH(5) PSD_YH(6) PSD_YH(7)
+            PSD_YH(8) PSD_YH(9) PSD_YH(10) PSD_YH(11) PSD_YH(12) PSD_YH(13) PSD_YH(14) PSD_YH(15)
+#undef PSD_YH
+        }
+    }
+#if PSD_WS_SYNCWARP
+    __syncwarp();  // all lanes' shared atomics / ring reads precede the arrival
+#endif
+    if (lane == 0) mbar_arrive_off<kWsStages * 8 + J * 8>(ad.full);
+}
+
+template <uint32_t F, int HV>
+__device__ __forceinline__ void ws_consume(const ScoreArgs& a, WsSmem& sm, int tid, int lane, int f0, int it_begin,
+                                           int it_end, int px0, int valid_px) {
+    constexpr int U = PSD_WS_UNROLL;
+    LutView lut{0u, 0u};
+    lut.s_addr = smem_u32(sm.lut) + lane * 4;
+    lut.h_addr = lut.s_addr + 128;
+    const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
+    const int my_px = px0 + tid * kPxPerThread;
+    const bool active = tid * kPxPerThread < valid_px;  // only the last strip has idle threads
+    // a zero the compiler cannot see through: it stays in one register for the whole loop instead of
+    // being re-materialised (CS2R) in front of every accumulation chain
+    const uint32_t zero = a.shift24 ^ 0x01000000u;
+    const uint32_t ring0 = smem_u32(sm.ring[0]) + tid * 48;
+    const uint32_t full0 = smem_u32(&sm.full[0]);
+    // threads without pixels add to the sink for the whole walk; everybody does for the frame without predecessor
+    const uint32_t acc0 = active ? smem_u32(&sm.accl[0][0][lane]) : smem_u32(&sm.accl_sink[0][0][lane]);
+    const uint32_t sink0 = smem_u32(&sm.accl_sink[0][0][lane]);
+#if PSD_WS_STAGGER
+    __nanosleep((unsigned)(tid >> 7) * PSD_WS_STAGGER);  // warp w sits on sub-partition w % 4, slot w / 4
+#endif
+    Px16 P0, P1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) P0.h[j] = P0.s[j] = P0.v[j] = P1.h[j] = P1.s[j] = P1.v[j] = 0;
+    const int n = it_end - it_begin;  // frames this CTA walks (halo included)
+    const int fbase = f0 - 1 + it_begin;  // frame index of k == 0
+    int k = 0;
+    int stage0 = 0;        // first stage of the current body
+    uint32_t parity = 0;
+    WsAddr ad{ring0, full0, acc0};
+    uint32_t acc_first = sink0;  // k == 0: no predecessor
+#pragma unroll 1
+    for (; k + U <= n; k += U) {
+        const bool first_mine = active && (it_begin + k >= 1);
+        ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, first_mine, fbase + k, my_px, lane, zero, lut, lut7, P0, P1);
+        ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+        if (U == 4) {
+            ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
+            ws_step<F, HV, 3 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 3, my_px, lane, zero, lut, lut7, P1, P0);
+        }
+        stage0 += U;
+        if (stage0 == kWsStages) {
+            stage0 = 0;
+            parity ^= 1u;
+            ad.ring = ring0; ad.full = full0; ad.acc = acc0;
+        } else {
+            ad.ring += U * kWsStripBytes; ad.full += U * 8; ad.acc += U * 512;
+        }
+        acc_first = ad.acc;
+    }
+    // tail: fewer than U frames left; the body always starts with P0 as the predecessor
+    if (k < n) {
+        ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, active && (it_begin + k >= 1), fbase + k, my_px, lane,
+                          zero, lut, lut7, P0, P1);
+        if (U == 4 && k + 1 < n) {
+            ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+            if (k + 2 < n)
+                ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
+        }
+    }
 }
 
 // HV selects the HSV arithmetic: 4 = scalar float LUT formulation (hsv_math.cuh), 7 = pixel pairs in
@@ -474,6 +666,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     }
 
     // ===================== consumer warps =====================
+#if PSD_WS_LOOP == 0
     LutView lut{0u, 0u};
     lut.s_addr = smem_u32(sm.lut) + lane * 4;
     lut.h_addr = lut.s_addr + 128;
@@ -571,6 +764,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         step(it + 1, P1, P0);
     }
     if (it < it_end) step(it, P0, P1);
+#else
+    ws_consume<F, HV>(a, sm, tid, lane, f0, it_begin, it_end, px0, valid_px);
+#endif
 }
 
 template <uint32_t F, int HV>
