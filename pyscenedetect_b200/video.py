@@ -35,6 +35,10 @@ class ArrayVideoStream:
     is_pinned = property(lambda self: self._pinned)
 
     @property
+    def base_timecode(self):
+        return FrameTimecode(0, self._fps)
+
+    @property
     def duration(self):
         return FrameTimecode(self._total, self._fps)
 

@@ -430,7 +430,7 @@ def test_scene_manager_plain_stream_crop_and_empty(lib):
     # crop
     sm2 = SceneManager(batch_size=8)
     sm2.auto_downscale = False
-    sm2.crop = (16, 10, 144, 82)
+    sm2.crop = (143, 10, 16, 81)     # inclusive corners in any order (scene_manager.py:293-306): x 16..143, y 10..81
     sm2.add_detector(ContentDetector())
     sm2.detect_scenes(_PlainStream(frames))
     cropped = np.ascontiguousarray(frames[:, 10:82, 16:144])

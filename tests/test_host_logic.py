@@ -108,11 +108,58 @@ def test_frame_by_frame_stream_and_crop_and_callback():
     want = [c for c in case["cuts"] if c < 200]
     assert [c.frame_num for c in sm.get_cut_list()] == want
     assert sorted(seen) == want  # callbacks fire for cuts inside the retained batch
+    # crop setter: inclusive corners in any order, stored one past the end (scene_manager.py:293-306)
+    sm.crop = (10, 10, 5, 20)
+    assert sm.crop == (5, 10, 10, 20) and sm._crop == (5, 10, 11, 21)
     with pytest.raises(ValueError):
-        sm.crop = (10, 10, 5, 20)
+        sm.crop = (-1, 0, 5, 5)
     with pytest.raises(TypeError):
         sm.crop = (1.0, 2, 3, 4)
+    # downscale setter keeps auto_downscale on and rejects 0 (scene_manager.py:313-325)
+    sm2 = SceneManager()
+    sm2.downscale = 3
+    assert sm2.auto_downscale is True and sm2.downscale == 3
+    with pytest.raises(ValueError):
+        sm2.downscale = 0
     assert isinstance(np.zeros(1), np.ndarray)
+
+
+@pytest.mark.parametrize("batch", [4, 7, 64])
+def test_callbacks_cross_batch_boundaries(batch):
+    """AdaptiveDetector reports a cut `window_width` frames behind the frame it is looking at and FlashFilter's
+    MERGE mode reports `_last_above`: both can sit in the previous batch (reference `_frame_buffer`,
+    scene_manager.py:422-434)."""
+    import numpy as np
+
+    from pyscenedetect_b200.detectors import AdaptiveDetector
+    from pyscenedetect_b200.scene_manager import SceneManager
+    from pyscenedetect_b200.video import ArrayVideoStream
+    case = get_case("adaptive_w2")
+    frames = case_frames(case)
+    seen = []
+    sm = SceneManager(batch_size=batch)
+    sm.auto_downscale = False
+    sm.add_detector(_build(case))
+    sm.detect_scenes(ArrayVideoStream(frames, case["fps"]),
+                     callback=lambda f, tc: seen.append((tc.frame_num, int(np.asarray(f, np.int64).sum()))))
+    cuts = [c.frame_num for c in sm.get_cut_list()]
+    assert cuts == case["cuts"] and len(cuts) >= 3
+    assert sorted(t for t, _ in seen) == cuts          # every cut got its callback ...
+    for t, total in seen:                              # ... with the frame of the cut, not a recycled buffer
+        assert total == int(frames[t].astype(np.int64).sum())
+    assert isinstance(AdaptiveDetector(), object)
+
+
+def test_kernel_size_agreement_only_among_edge_detectors():
+    from pyscenedetect_b200.detectors import ContentDetector, ThresholdDetector
+    from pyscenedetect_b200.scene_manager import SceneManager
+    from pyscenedetect_b200.video import ArrayVideoStream
+    frames = case_frames(get_case("content_default_nostats"))[:20]
+    sm = SceneManager(batch_size=8)
+    sm.auto_downscale = False
+    sm.add_detector(ContentDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 0.5), kernel_size=5))
+    sm.add_detector(ThresholdDetector())   # owns no dilation kernel: must not clash with kernel_size=5
+    assert sm.detect_scenes(ArrayVideoStream(frames, 30.0)) == 20
 
 
 def test_plain_stream_crop_empty_host_logic(monkeypatch):
