@@ -52,8 +52,9 @@ struct ScoreArgs {
     int64_t frame_stride;
     int32_t n_frames;
     int32_t n_pixels;        // W*H
-    int32_t chunk_frames;    // frames per time chunk
-    int32_t n_chunks;
+    int32_t chunk_frames;    // frames per time chunk (generic kernel)
+    int32_t n_chunks;        // time chunks (the persistent kernel splits the frames into n_chunks near-equal runs)
+    uint32_t features;       // PSD_F_* mask of the launch (device-side copy of the template argument)
     int32_t n_strips;
     int32_t tma_ok;          // base pointers and stride 16-byte aligned
     int32_t px_base;         // first pixel this launch covers (strips are relative to it)

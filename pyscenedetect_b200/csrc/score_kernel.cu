@@ -294,14 +294,26 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 
 
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised form of the same pass (full, 16-byte aligned strips only).
-// 24 consumer warps + 1 producer warp per CTA, one CTA per SM, no CTA-wide barrier in the frame
-// loop: consumers wait on the stage's FULL mbarrier (TMA complete_tx), pull their 48 bytes, do the
-// arithmetic, add their warp-reduced partials to the stage's shared accumulators and arrive on the
-// stage's EMPTY mbarrier; the producer warp waits for all 24 arrivals, flushes the stage's
-// accumulators / histogram bins to HBM with integer atomics, zeroes them and immediately re-arms
-// the stage with the bulk copy of the frame three iterations ahead.  Warps can therefore drift up
-// to kWsStages frames apart instead of meeting at a __syncthreads every frame.
+// Warp-specialised, persistent form of the same pass (full, 16-byte aligned strips only).
+//
+// One CTA per SM for the whole launch: 24 consumer warps + 1 producer warp.  The work is cut into items
+// (strip of 12288 pixels x chunk of consecutive frames); CTA b walks items b, b + grid, b + 2 grid, ...
+// Frames travel global->shared by 1-D bulk TMA into a 4-stage ring whose stage sequence simply continues
+// from one item into the next, so the producer is always kWsStages frames ahead - also across item
+// boundaries: there is no pipeline fill / drain per item, the LUT is built once per SM and no SM idles
+// between CTAs (the non-persistent form lost ~4 % of the SM time between CTAs and ~5 % of the warp time
+// waiting for the first frame of each CTA: profiles/r02a_*).
+//
+// No CTA-wide barrier in the frame loop: consumers wait on the stage's FULL mbarrier (TMA complete_tx),
+// pull their 48 bytes, do the arithmetic, add their SADs to the stage's per-lane shared accumulators and
+// arrive on the stage's EMPTY mbarrier; the producer warp waits for the 24 arrivals, reads the stage's
+// totals, re-arms the stage with the frame kWsStages slots ahead and then flushes the totals / histogram
+// bins of the retired frame to HBM with integer atomics.
+//
+// An item whose frame count is not a multiple of the consumer loop's unroll factor is padded with null
+// slots (the producer completes the FULL barrier without a copy, the consumers only arrive), so a loop
+// body always starts at a stage that is a multiple of the unroll factor and every stage offset inside
+// the body is an immediate.
 // ---------------------------------------------------------------------------------------------
 // 24 consumer warps = 6 per sub-partition (25 was measured 4.5 % slower: 7/6/6/6 is unbalanced).
 // A last, partial strip is handled in the same kernel when it is a whole number of 16-pixel
@@ -312,18 +324,30 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 #ifndef PSD_WS_STAGES
 #define PSD_WS_STAGES 4
 #endif
+#ifndef PSD_WS_UNROLL
+#define PSD_WS_UNROLL 2  // frames per consumer loop body: 2 (stage pair toggles) or 4 (all stage offsets immediate)
+#endif
+#ifndef PSD_WS_SYNCWARP
+// 0: no __syncwarp() in front of lane 0's EMPTY arrival.  The warp is converged there (every branch of the
+// step is closed by the compiler's BSSY/BSYNC pair), its lanes' LDS results were consumed by the arithmetic
+// above and its shared REDs entered the same in-order shared-memory pipe before the arrival does; the
+// convergence check costs UMOV + BRA.DIV + NOP + three register copies per frame.
+#define PSD_WS_SYNCWARP 0
+#endif
 constexpr int kWsConsumerWarps = PSD_WS_WARPS;
 constexpr int kWsConsumers = kWsConsumerWarps * 32;  // 768
 constexpr int kWsThreads = kWsConsumers + 32;        // + producer warp
 constexpr int kWsStages = PSD_WS_STAGES;
+constexpr int kWsUnroll = PSD_WS_UNROLL;
 constexpr int kWsStripPx = kWsConsumers * kPxPerThread;  // 12288 pixels
 constexpr int kWsStripBytes = kWsStripPx * 3;            // 36864 bytes
+static_assert(kWsStages % kWsUnroll == 0, "the stage ring must be a whole number of loop bodies");
 
 struct __align__(128) WsSmem {
     uint8_t ring[kWsStages][kWsStripBytes];
     float lut[256 * 64];
     unsigned long long full[kWsStages];
-    unsigned long long empty[kWsStages];
+    unsigned long long empty[kWsStages];   // must follow `full` (addressed as full + kWsStages * 8)
     // per-lane running totals of sadH, sadS, sadV, bgr: every consumer thread adds its partial to the
     // word of ITS lane (32 distinct banks: one conflict-free red.shared per channel per thread, no
     // warp reduction, no election).  Never zeroed: the producer keeps the totals it saw last and
@@ -340,64 +364,8 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
     asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
-__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 // try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase
 // completes instead of burning issue slots of its sub-partition in a poll loop
-__device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(20000u)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// ---- consumer side, second form (PSD_WS_LOOP 1, the default) -------------------------------------
-// Same arithmetic as the first form; what changed is everything around it, because the pass is
-// issue-bound and ~10 % of the first loop's issue slots were bookkeeping:
-//   * the ring has 4 stages and the loop body covers PSD_WS_UNROLL (2 or 4) frames, so a frame's stage
-//     is a compile-time offset from one base register per body (ring, barrier, accumulator addresses
-//     are [reg + immediate] operands instead of IMAD/LEA/SEL chains per frame);
-//   * the SADs are always computed and only the three shared adds are predicated (no BSSY/BRA/BSYNC
-//     around them); the first frame of a chunk, which has no predecessor, just wastes 12 VABSDIFF4;
-//   * the wait parity flips once per ring revolution instead of a compare + select per frame.
-#ifndef PSD_WS_LOOP
-#define PSD_WS_LOOP 1
-#endif
-#ifndef PSD_WS_UNROLL
-#define PSD_WS_UNROLL 2
-#endif
-#ifndef PSD_WS_SYNCWARP
-// 0: no __syncwarp() in front of lane 0's EMPTY arrival.  The warp is converged there (every branch of the
-// step is closed by the compiler's BSSY/BSYNC pair), its lanes' LDS results were consumed by the arithmetic
-// above and its shared REDs entered the same in-order shared-memory pipe before the arrival does; the
-// convergence check costs UMOV + BRA.DIV + NOP + three register copies per frame.
-#define PSD_WS_SYNCWARP 0
-#endif
-#ifndef PSD_WS_STAGGER
-#define PSD_WS_STAGGER 0  // ns of start-up delay per warp slot of a sub-partition (de-phases its warps)
-#endif
-#if PSD_WS_LOOP
-static_assert(kWsStages % PSD_WS_UNROLL == 0, "the stage ring must be a whole number of loop bodies");
-#endif
-
-struct WsAddr {  // shared-window addresses of the current loop body's first stage
-    uint32_t ring;   // + tid * 48
-    uint32_t full;   // FULL mbarrier of the stage; EMPTY mbarriers follow kWsStages * 8 bytes later
-    uint32_t acc;    // per-lane accumulators of the stage (this lane's word of channel 0)
-};
-
 template <int OFF>
 __device__ __forceinline__ void mbar_wait_hint_off(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -412,6 +380,9 @@ __device__ __forceinline__ void mbar_wait_hint_off(uint32_t bar, uint32_t parity
         "r"(parity), "r"(20000u), "n"(OFF)
         : "memory");
 }
+__device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, uint32_t parity) {
+    mbar_wait_hint_off<0>(smem_u32(bar), parity);
+}
 template <int OFF>
 __device__ __forceinline__ void lds128_off(uint32_t addr, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr), "n"(OFF));
@@ -424,6 +395,42 @@ template <int OFF>
 __device__ __forceinline__ void mbar_arrive_off(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(bar), "n"(OFF) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- work decomposition shared by host, producer and consumers ----
+// chunk c covers frames [c * N / C, (c + 1) * N / C): sizes differ by at most one frame
+__host__ __device__ __forceinline__ int chunk_first(int c, int n_frames, int n_chunks) {
+    return (int)(((long long)c * n_frames) / n_chunks);
+}
+struct WsItem {  // one (strip, chunk) of the launch
+    int f0, nf;          // first frame, frames
+    int px0, valid_px;   // first pixel, pixels (a multiple of 16)
+    int it_begin;        // 0: the walk starts with the predecessor (halo) frame, 1: it has none
+    int slots;           // frames walked, padded to a multiple of the unroll factor
+    int walked;          // frames walked (halo included)
+};
+__device__ __forceinline__ WsItem ws_item(const ScoreArgs& a, int item) {
+    WsItem w;
+    const int chunk = item % a.n_chunks;  // chunk-fastest: CTAs running side by side are on different frames
+    const int strip = item / a.n_chunks;
+    w.f0 = chunk_first(chunk, a.n_frames, a.n_chunks);
+    w.nf = chunk_first(chunk + 1, a.n_frames, a.n_chunks) - w.f0;
+    w.px0 = strip * kWsStripPx;
+    w.valid_px = min(kWsStripPx, a.n_pixels - w.px0);
+    const bool have_halo = (a.features & PSD_F_HSV) && (w.f0 > 0 || a.prev != nullptr);
+    w.it_begin = have_halo ? 0 : 1;
+    w.walked = w.nf + 1 - w.it_begin;
+    w.slots = (w.walked + kWsUnroll - 1) / kWsUnroll * kWsUnroll;
+    return w;
+}
+
+struct WsAddr {  // shared-window addresses of the current loop body's first stage
+    uint32_t ring;   // + tid * 48
+    uint32_t full;   // FULL mbarrier of the stage; EMPTY mbarriers follow kWsStages * 8 bytes later
+    uint32_t acc;    // per-lane accumulators of the stage (this lane's word of channel 0; or the sink's)
+};
 
 // One frame of the consumer loop at stage (body base + J).  `sad_acc`: accumulator base the SADs go to (the
 // stage's real per-lane words, or the sink); `mine`: the frame is not the halo and the thread owns pixels.
@@ -437,7 +444,7 @@ __device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const Ws
     constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
     mbar_wait_hint_off<J * 8>(ad.full, parity);
     uint32_t w[12];
-    // idle threads of a partial last strip read stale ring bytes; they never contribute (add_sad / mine)
+    // idle threads of a partial last strip read stale ring bytes; they never contribute (sink / mine)
     lds128_off<J * kWsStripBytes>(ad.ring, w[0], w[1], w[2], w[3]);
     lds128_off<J * kWsStripBytes + 16>(ad.ring, w[4], w[5], w[6], w[7]);
     lds128_off<J * kWsStripBytes + 32>(ad.ring, w[8], w[9], w[10], w[11]);
@@ -492,66 +499,11 @@ __device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const Ws
     if (lane == 0) mbar_arrive_off<kWsStages * 8 + J * 8>(ad.full);
 }
 
-template <uint32_t F, int HV>
-__device__ __forceinline__ void ws_consume(const ScoreArgs& a, WsSmem& sm, int tid, int lane, int f0, int it_begin,
-                                           int it_end, int px0, int valid_px) {
-    constexpr int U = PSD_WS_UNROLL;
-    LutView lut{0u, 0u};
-    lut.s_addr = smem_u32(sm.lut) + lane * 4;
-    lut.h_addr = lut.s_addr + 128;
-    const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
-    const int my_px = px0 + tid * kPxPerThread;
-    const bool active = tid * kPxPerThread < valid_px;  // only the last strip has idle threads
-    // a zero the compiler cannot see through: it stays in one register for the whole loop instead of
-    // being re-materialised (CS2R) in front of every accumulation chain
-    const uint32_t zero = a.shift24 ^ 0x01000000u;
-    const uint32_t ring0 = smem_u32(sm.ring[0]) + tid * 48;
-    const uint32_t full0 = smem_u32(&sm.full[0]);
-    // threads without pixels add to the sink for the whole walk; everybody does for the frame without predecessor
-    const uint32_t acc0 = active ? smem_u32(&sm.accl[0][0][lane]) : smem_u32(&sm.accl_sink[0][0][lane]);
-    const uint32_t sink0 = smem_u32(&sm.accl_sink[0][0][lane]);
-#if PSD_WS_STAGGER
-    __nanosleep((unsigned)(tid >> 7) * PSD_WS_STAGGER);  // warp w sits on sub-partition w % 4, slot w / 4
-#endif
-    Px16 P0, P1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) P0.h[j] = P0.s[j] = P0.v[j] = P1.h[j] = P1.s[j] = P1.v[j] = 0;
-    const int n = it_end - it_begin;  // frames this CTA walks (halo included)
-    const int fbase = f0 - 1 + it_begin;  // frame index of k == 0
-    int k = 0;
-    int stage0 = 0;        // first stage of the current body
-    uint32_t parity = 0;
-    WsAddr ad{ring0, full0, acc0};
-    uint32_t acc_first = sink0;  // k == 0: no predecessor
-#pragma unroll 1
-    for (; k + U <= n; k += U) {
-        const bool first_mine = active && (it_begin + k >= 1);
-        ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, first_mine, fbase + k, my_px, lane, zero, lut, lut7, P0, P1);
-        ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
-        if (U == 4) {
-            ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
-            ws_step<F, HV, 3 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 3, my_px, lane, zero, lut, lut7, P1, P0);
-        }
-        stage0 += U;
-        if (stage0 == kWsStages) {
-            stage0 = 0;
-            parity ^= 1u;
-            ad.ring = ring0; ad.full = full0; ad.acc = acc0;
-        } else {
-            ad.ring += U * kWsStripBytes; ad.full += U * 8; ad.acc += U * 512;
-        }
-        acc_first = ad.acc;
-    }
-    // tail: fewer than U frames left; the body always starts with P0 as the predecessor
-    if (k < n) {
-        ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, active && (it_begin + k >= 1), fbase + k, my_px, lane,
-                          zero, lut, lut7, P0, P1);
-        if (U == 4 && k + 1 < n) {
-            ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
-            if (k + 2 < n)
-                ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
-        }
-    }
+// A padding slot: nothing was copied, the consumers only hand the stage back.
+template <int J>
+__device__ __forceinline__ void ws_null_step(const WsAddr& ad, uint32_t parity, int lane) {
+    mbar_wait_hint_off<J * 8>(ad.full, parity);
+    if (lane == 0) mbar_arrive_off<kWsStages * 8 + J * 8>(ad.full);
 }
 
 // HV selects the HSV arithmetic: 4 = scalar float LUT formulation (hsv_math.cuh), 7 = pixel pairs in
@@ -564,24 +516,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
     constexpr bool kYH = (F & PSD_F_YHIST) != 0;
     constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
+    constexpr int U = kWsUnroll;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int chunk = blockIdx.x % a.n_chunks;
-    const int strip = blockIdx.x / a.n_chunks;
-    const int f0 = chunk * a.chunk_frames;
-    const int nf = min(a.chunk_frames, a.n_frames - f0);
-    const int px0 = strip * kWsStripPx;
-    const int valid_px = min(kWsStripPx, a.n_pixels - px0);  // a multiple of 16 (launch_score checks)
-    const uint32_t copy_bytes = (uint32_t)valid_px * 3u;     // hence a multiple of 48
-    const bool have_halo = kHSV && (f0 > 0 || a.prev != nullptr);
-    const int it_begin = have_halo ? 0 : 1;
-    const int it_end = nf + 1;
-    const int64_t strip_off = (int64_t)px0 * 3;
-    auto frame_ptr = [&](int it) -> const uint8_t* {
-        const int fi = f0 - 1 + it;
-        return (fi < 0 ? a.prev : a.frames + (int64_t)fi * a.frame_stride) + strip_off;
-    };
+    const int n_items = a.n_chunks * a.n_strips;
 
     for (int i = tid; i < kWsStages * 256; i += kWsThreads) {
         (&sm.yhist[0][0])[i] = 0;
@@ -590,6 +529,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     for (int i = tid; i < kWsStages * 4 * 32; i += kWsThreads) {
         (&sm.accl[0][0][0])[i] = 0;
         (&sm.accl_seen[0][0][0])[i] = 0;
+        (&sm.accl_sink[0][0][0])[i] = 0;
     }
     if (kHSV) {
         if (HV >= 7) lut_fill7(sm.lut, tid, kWsThreads);
@@ -606,26 +546,51 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
 
     if (tid >= kWsConsumers) {
         // ===================== producer warp =====================
-        if (lane == 0) {
-            for (int s = 0; s < kWsStages && it_begin + s < it_end; ++s) {
-                mbar_expect_tx(&sm.full[s], copy_bytes);
-                bulk_g2s(sm.ring[s], frame_ptr(it_begin + s), copy_bytes, &sm.full[s]);
+        // Two cursors over the same slot sequence (items of this CTA, slots of each item): `iss` is the slot
+        // whose copy is issued next, `ret` the slot retired next; iss runs kWsStages slots ahead of ret.
+        struct Cursor {
+            int item, slot;
+            WsItem w;
+        };
+        auto load = [&](Cursor& c) { if (c.item < n_items) c.w = ws_item(a, c.item); };
+        auto advance = [&](Cursor& c) {
+            if (++c.slot == c.w.slots) { c.slot = 0; c.item += gridDim.x; load(c); }
+        };
+        auto issue = [&](const Cursor& c, int stage) {  // lane 0 only
+            if (c.slot < c.w.walked) {
+                const int fi = c.w.f0 - 1 + c.w.it_begin + c.slot;
+                const uint8_t* src = (fi < 0 ? a.prev : a.frames + (int64_t)fi * a.frame_stride) + (int64_t)c.w.px0 * 3;
+                const uint32_t bytes = (uint32_t)c.w.valid_px * 3u;
+                mbar_expect_tx(&sm.full[stage], bytes);
+                bulk_g2s(sm.ring[stage], src, bytes, &sm.full[stage]);
+            } else {
+                mbar_arrive(&sm.full[stage]);  // padding slot: complete the phase without a copy
             }
+        };
+        Cursor iss{(int)blockIdx.x, 0, {}}, ret{(int)blockIdx.x, 0, {}};
+        load(iss);
+        ret.w = iss.w;
+        for (int s = 0; s < kWsStages && iss.item < n_items; ++s) {
+            if (lane == 0) issue(iss, s);
+            advance(iss);
         }
         int stage = 0;
         uint32_t parity = 0;
-        for (int it = it_begin; it < it_end; ++it) {
+        while (ret.item < n_items) {
             mbar_wait_hint(&sm.empty[stage], parity);
-            const int fi = f0 - 1 + it;
+            const int it = ret.w.it_begin + ret.slot;             // 0 = halo frame
+            const bool real = ret.slot < ret.w.walked;
+            const bool own = real && it >= 1;                     // this CTA accounts for frame fi
+            const int fi = ret.w.f0 - 1 + it;
             // the per-lane totals are read BEFORE the stage is re-armed: no consumer can add the next
             // frame of this stage to them until the copy issued below has landed
             uint32_t tot[4] = {0u, 0u, 0u, 0u};
-            if (it >= 1 && (kHSV || kSUM)) {
+            if (own && (kHSV || kSUM)) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if ((c < 3 && kHSV) || (c == 3 && kSUM)) tot[c] = sm.accl[stage][c][lane];
             }
-            if (it >= 1) {  // this CTA accounts for frame fi (not the halo)
+            if (own) {
                 if (kYH) {
 #pragma unroll
                     for (int b = lane; b < 256; b += 32) {
@@ -640,15 +605,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
                         if (v) { sm.vhist[stage][b] = 0; atomicAdd(&a.vhist[(int64_t)fi * 256 + b], v); }
                     }
                 }
-                if (a.write_has_prev && strip == 0 && lane == 0)
+                if (a.write_has_prev && ret.w.px0 == 0 && lane == 0)
                     a.sums[fi].has_prev = (fi > 0 || a.prev != nullptr) ? 1ull : 0ull;
             }
             __syncwarp();  // the histogram zeroing above is ordered before lane 0 re-arms the stage
-            if (lane == 0 && it + kWsStages < it_end) {
-                mbar_expect_tx(&sm.full[stage], copy_bytes);
-                bulk_g2s(sm.ring[stage], frame_ptr(it + kWsStages), copy_bytes, &sm.full[stage]);
+            if (iss.item < n_items) {
+                if (lane == 0) issue(iss, stage);
+                advance(iss);
             }
-            if (it >= 1 && (kHSV || kSUM)) {  // after the re-arm: the copy engine's queue is fed first
+            if (own && (kHSV || kSUM)) {  // after the re-arm: the copy engine's queue is fed first
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if ((c < 3 && !kHSV) || (c == 3 && !kSUM)) continue;
@@ -660,124 +625,116 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
                                   (unsigned long long)v);
                 }
             }
+            advance(ret);
             if (++stage == kWsStages) { stage = 0; parity ^= 1u; }
         }
         return;
     }
 
     // ===================== consumer warps =====================
-#if PSD_WS_LOOP == 0
     LutView lut{0u, 0u};
     lut.s_addr = smem_u32(sm.lut) + lane * 4;
     lut.h_addr = lut.s_addr + 128;
     const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
-    const int my_px = px0 + tid * kPxPerThread;
-    const bool active = tid * kPxPerThread < valid_px;  // only the last strip has idle threads
-    const uint32_t accl_addr = smem_u32(&sm.accl[0][0][lane]);
-    const uint32_t ring_addr = smem_u32(sm.ring[0]) + tid * 48;
-    bool prev_valid = false;
-    int stage = 0;
-    uint32_t parity = 0;
     // a zero the compiler cannot see through: it stays in one register for the whole loop instead of
     // being re-materialised (CS2R) in front of every accumulation chain
     const uint32_t zero = a.shift24 ^ 0x01000000u;
-
-    // One frame: wait for the stage, pull this thread's 48 bytes, score them against `prev`, leave the
-    // planes in `cur`.  Called alternately with (P0, P1) and (P1, P0), so the previous frame's planes
-    // never have to be copied between registers.
-    auto step = [&](const int it, const Px16& prev, Px16& cur) {
-        mbar_wait_hint(&sm.full[stage], parity);
-        uint32_t w[12];
-        {   // idle threads of a partial last strip read stale ring bytes; they never contribute (see `mine`)
-            const uint32_t ra = ring_addr + stage * kWsStripBytes;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ra));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(ra));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]) : "r"(ra));
+    const uint32_t ring0 = smem_u32(sm.ring[0]) + tid * 48;
+    const uint32_t full0 = smem_u32(&sm.full[0]);
+    const uint32_t accl0 = smem_u32(&sm.accl[0][0][lane]);
+    const uint32_t sink0 = smem_u32(&sm.accl_sink[0][0][lane]);
+    int stage0 = 0;        // first stage of the current body
+    uint32_t parity = 0;
+    WsAddr ad{ring0, full0, 0u};
+    auto next_body = [&](uint32_t acc0) {
+        stage0 += U;
+        if (stage0 == kWsStages) {
+            stage0 = 0;
+            parity ^= 1u;
+            ad.ring = ring0; ad.full = full0; ad.acc = acc0;
+        } else {
+            ad.ring += U * kWsStripBytes; ad.full += U * 8; ad.acc += U * 512;
         }
-        const int fi = f0 - 1 + it;
-        const bool own = (it >= 1);
-        const bool mine = own && active;
-        const uint32_t acc_stage = accl_addr + stage * (4 * 32 * 4);
-        if (kHSV) {
-#ifdef PSD_WS_PAIR_V4
-            hsv16_v4pair(w, cur, lut);  // FADD2/FFMA2 on pixel pairs: 12 % fewer issue slots, but measured
-                                        // 1 % slower in the kernel and 5 % slower compute-only (pipe-bound)
-#else
-            if (HV >= 7) hsv16_v7<HV == 8>(w, cur, lut7, a.shift24);
-            else hsv16_v4(w, cur, lut);
-#endif
-            if (prev_valid && mine) {
-                // one dependent VABSDIFF4.ACC chain per plane (the compiler otherwise splits each into
-                // four zero-seeded accumulators plus an IADD3 tree: 12 extra issue slots per frame)
-                uint32_t sad_h = sad4_acc(cur.h[0], prev.h[0], zero), sad_s = sad4_acc(cur.s[0], prev.s[0], zero),
-                         sad_v = sad4_acc(cur.v[0], prev.v[0], zero);
-#pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    sad_h = sad4_acc(cur.h[j], prev.h[j], sad_h);
-                    sad_s = sad4_acc(cur.s[j], prev.s[j], sad_s);
-                    sad_v = sad4_acc(cur.v[j], prev.v[j], sad_v);
-                }
-                red_shared_add(acc_stage, sad_h);
-                red_shared_add(acc_stage + 128, sad_s);
-                red_shared_add(acc_stage + 256, sad_v);
-            }
-            prev_valid = true;
-            if (kEDGE && mine) {
-                uint8_t* vp = a.vplane + (int64_t)fi * a.n_pixels + my_px;
-                if ((a.n_pixels & 15) == 0) {
-                    *reinterpret_cast<uint4*>(vp) = make_uint4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
-                } else {
-                    for (int p = 0; p < kPxPerThread; ++p) vp[p] = (uint8_t)(cur.v[p >> 2] >> ((p & 3) * 8));
-                }
-#pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p)
-                    atomicAdd(&sm.vhist[stage][(cur.v[p >> 2] >> ((p & 3) * 8)) & 0xFF], 1u);
-            }
-        }
-        if (mine) {
-            if (kSUM) {
-                uint32_t bsum = 0;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) bsum = __dp4a(w[j], 0x01010101u, bsum);
-                red_shared_add(acc_stage + 384, bsum);
-            }
-            if (kYH) {
-                uint32_t* hist = sm.yhist[stage];
-#define PSD_YH(i) atomicAdd(&hist[y_of_pixel<i>(w)], 1u);
-                PSD_YH(0) PSD_YH(1) PSD_YH(2) PSD_YH(3) PSD_YH(4) PSD_YH(5) PSD_YH(6) PSD_YH(7)
-                PSD_YH(8) PSD_YH(9) PSD_YH(10) PSD_YH(11) PSD_YH(12) PSD_YH(13) PSD_YH(14) PSD_YH(15)
-#undef PSD_YH
-            }
-        }
-        __syncwarp();  // all lanes' shared atomics / ring reads precede the arrival
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
-        if (++stage == kWsStages) { stage = 0; parity ^= 1u; }
     };
-
-    Px16 P0, P1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WsItem wi = ws_item(a, item);
+        const int my_px = wi.px0 + tid * kPxPerThread;
+        const bool active = tid * kPxPerThread < wi.valid_px;  // only the last strip has idle threads
+        // threads without pixels add to the sink for the whole walk; everybody does for the frame without predecessor
+        const uint32_t acc0 = active ? accl0 : sink0;
+        ad.acc = acc0 + stage0 * 512;
+        Px16 P0, P1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) P0.h[j] = P0.s[j] = P0.v[j] = P1.h[j] = P1.s[j] = P1.v[j] = 0;
-    int it = it_begin;
+        for (int j = 0; j < 4; ++j) P0.h[j] = P0.s[j] = P0.v[j] = P1.h[j] = P1.s[j] = P1.v[j] = 0;
+        const int n = wi.walked;                      // frames walked (halo included)
+        const int fbase = wi.f0 - 1 + wi.it_begin;    // frame index of k == 0
+        int k = 0;
+        uint32_t acc_first = sink0 + stage0 * 512;    // k == 0: no predecessor
 #pragma unroll 1
-    for (; it + 1 < it_end; it += 2) {
-        step(it, P0, P1);
-        step(it + 1, P1, P0);
+        for (; k + U <= n; k += U) {
+            const bool first_mine = active && (wi.it_begin + k >= 1);
+            ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, first_mine, fbase + k, my_px, lane, zero, lut, lut7, P0, P1);
+            ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+            if (U == 4) {
+                ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
+                ws_step<F, HV, 3 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 3, my_px, lane, zero, lut, lut7, P1, P0);
+            }
+            next_body(acc0);
+            acc_first = ad.acc;
+        }
+        if (k < n) {  // last, partial body of the item: real frames first, then the padding slots
+            const int r = n - k;  // 1 .. U-1
+            ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, active && (wi.it_begin + k >= 1), fbase + k, my_px,
+                              lane, zero, lut, lut7, P0, P1);
+            if (U == 4) {
+                if (r > 1) ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+                else ws_null_step<1>(ad, parity, lane);
+                if (r > 2) ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
+                else ws_null_step<2 % U>(ad, parity, lane);
+                ws_null_step<3 % U>(ad, parity, lane);
+            } else {
+                ws_null_step<1>(ad, parity, lane);
+            }
+            next_body(acc0);
+        }
     }
-    if (it < it_end) step(it, P0, P1);
-#else
-    ws_consume<F, HV>(a, sm, tid, lane, f0, it_begin, it_end, px0, valid_px);
-#endif
+}
+
+// Number of time chunks: the walk costs (frames + 1 halo) per item and the launch ends when the most
+// loaded SM is done, so minimise ceil(strips * C / grid) * (N / C + 1) over C.
+static int pick_chunks(int n_frames, int n_strips, int grid) {
+    long long best_cost = -1;
+    int best = 1;
+    const int c_max = n_frames < 4096 ? n_frames : 4096;
+    for (int c = 1; c <= c_max; ++c) {
+        const int longest = (n_frames + c - 1) / c;
+        if (longest < 8 && c > 1) break;  // shorter walks only add halo frames
+        const long long per_cta = ((long long)n_strips * c + grid - 1) / grid;
+        const long long cost = per_cta * (longest + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
 }
 
 template <uint32_t F, int HV>
 static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
     const int smem = (int)sizeof(WsSmem);
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        PSD_CUDA(cudaGetDevice(&dev));
+        PSD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
     PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     a.shift24 = 0x01000000u;
+    a.features = F;
     a.n_strips = n_ws_strips;
-    const int64_t grid = (int64_t)a.n_chunks * n_ws_strips;
-    PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
-    psd_score_ws_kernel<F, HV><<<(unsigned)grid, kWsThreads, smem, stream>>>(a);
+    if (a.n_chunks <= 0) a.n_chunks = pick_chunks(a.n_frames, n_ws_strips, sm_count);
+    if (a.n_chunks > a.n_frames) a.n_chunks = a.n_frames;
+    const int64_t items = (int64_t)a.n_chunks * n_ws_strips;
+    PSD_REQUIRE(items > 0 && items < 2147483647LL, "score work items out of range (%lld)", (long long)items);
+    const int grid = (int)(items < sm_count ? items : sm_count);
+    psd_score_ws_kernel<F, HV><<<grid, kWsThreads, smem, stream>>>(a);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;
@@ -828,21 +785,18 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
     ScoreArgs a = a_in;
     if (features & PSD_F_EDGES) features |= PSD_F_HSV;
     PSD_REQUIRE(a.n_frames > 0 && a.n_pixels > 0, "empty score launch");
-    if (a.chunk_frames <= 0) {
-        // Longer time chunks amortise the per-CTA prologue (LUT fill, first TMA) and the recomputed
-        // halo frame (1/chunk); keep at least ~16 waves of CTAs on the 148 SMs.
-        const int64_t strips = (a.n_pixels + kWsStripPx - 1) / kWsStripPx;
-        a.chunk_frames = (strips * (a.n_frames / 128) >= 148 * 16) ? 128 : 64;
-        if (const char* c = getenv("PSD_CHUNK_FRAMES")) a.chunk_frames = atoi(c) > 0 ? atoi(c) : a.chunk_frames;
-    }
-    a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.frames) | (uintptr_t)a.frame_stride |
                          reinterpret_cast<uintptr_t>(a.prev);
     a.tma_ok = ((al & 15) == 0) ? 1 : 0;
     a.px_base = 0;
     a.write_has_prev = 1;
+    // generic kernel: fixed-length time chunks (one CTA per strip x chunk)
+    auto generic_chunks = [&](int frames_per_chunk) {
+        a.chunk_frames = frames_per_chunk;
+        a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
+    };
     if (variant == 5 || variant == 7 || variant == 8) {
-        // warp-specialised kernel on the 12288-pixel strips, generic kernel (variant 2) on
+        // persistent warp-specialised kernel on the 12288-pixel strips, generic kernel (variant 2) on
         // the remainder; an unaligned input goes entirely through the generic kernel
         int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
         int covered = n_ws * kWsStripPx;
@@ -852,17 +806,20 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
             covered = a.n_pixels;
         }
         if (n_ws > 0) {
+            a.n_chunks = 0;  // launch_ws balances the time chunks over the SMs
+            if (const char* c = getenv("PSD_CHUNKS")) a.n_chunks = atoi(c) > 0 ? atoi(c) : 0;
             int rc = dispatch_ws(a, features, variant == 5 ? 4 : variant, n_ws, stream);
             if (rc) return rc;
             a.px_base = covered;
             a.write_has_prev = 0;
             if (a.px_base >= a.n_pixels) return PSD_OK;
-            // the remainder is a sliver of the frame: shorter time chunks give it enough CTAs
-            a.chunk_frames = 16;
-            a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
+            generic_chunks(16);  // the remainder is a sliver of the frame: short time chunks give it enough CTAs
+        } else {
+            generic_chunks(64);
         }
         return dispatch<2>(a, features, stream);
     }
+    generic_chunks(64);
     // variant 1: scalar integer + MUFU (first correct version), 2: packed f32x2, 4: float LUT
     switch (variant) {
         case 1: return dispatch<1>(a, features, stream);
