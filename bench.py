@@ -48,7 +48,14 @@ def parse_args():
                          "scratch - V plane, class map, union-find labels - is 6 B/px per frame of a batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--detector", default="content", choices=["content", "content_edges", "threshold", "histogram"])
+    ap.add_argument("--detector", default="content",
+                    choices=["content", "content_edges", "adaptive", "threshold", "histogram"],
+                    help="adaptive = BASELINE.json configs[2]: edge component + AdaptiveDetector(window_width=5)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU; strong: --frames in total, split into contiguous time shards")
+    ap.add_argument("--parity-frames", type=int, default=None,
+                    help="frames of the timed run re-scored with the oracle (default: the cpu sample, 48 with --no-cpu)")
+    ap.add_argument("--ref-frames-per-proc", type=int, default=64, help="reference arm: frames per process per step")
     ap.add_argument("--auto-downscale", action="store_true",
                     help="score at SceneManager's default auto-downscaled size (256 px wide) instead of full resolution")
     return ap.parse_args()
@@ -135,8 +142,11 @@ def measured_peak_gbs() -> tuple[float, str]:
 # detector configuration per --detector
 # ------------------------------------------------------------------------------------------
 def detector_setup(kind: str):
-    from pyscenedetect_b200.detectors import ContentDetector, HistogramDetector, ThresholdDetector
+    from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector, ThresholdDetector
     from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST
+    if kind == "adaptive":
+        return F_HSV | F_EDGES, (lambda: AdaptiveDetector(window_width=5, weights=ContentDetector.Components(1, 1, 1, 1))), \
+            "AdaptiveDetector(window_width=5, weights=(1,1,1,1)) [edge component on]"
     if kind == "content":
         return F_HSV, (lambda: ContentDetector()), "ContentDetector() defaults: weights (1,1,1,0), threshold 27"
     if kind == "content_edges":
@@ -151,6 +161,8 @@ def ref_detector(kind: str):
     from oracle import ref_detectors as R
     if kind == "content":
         return R.RefContentDetector()
+    if kind == "adaptive":
+        return R.RefAdaptiveDetector(window_width=5, weights=(1.0, 1.0, 1.0, 1.0))
     if kind == "content_edges":
         return R.RefContentDetector(weights=(1.0, 1.0, 1.0, 1.0))
     if kind == "threshold":
@@ -200,47 +212,84 @@ def _ref_run_pool(kind, n_proc, per_proc, w, h, seed, rounds):
 
 
 def run_reference(args):
-    """Time shards over all host cores, one process per core, cv2 single-threaded in each
-    (BASELINE.md §3 variant ii).  A step is a bounded sample: `cores * per_core` frames."""
-    import multiprocessing as mp
+    """Time shards over the host cores, one process per shard, cv2 single-threaded in each
+    (BASELINE.md §3 variant ii).  A step is a bounded sample: `n_proc * per_proc` frames.
+    The process count comes from a WARM probe (2 untimed + 1 timed round of 16 frames per process) over a few
+    candidates; the timed steps then run >= 64 frames per process so that a step lasts seconds, not tenths."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per_core = 8
+    per_proc = max(8, int(args.ref_frames_per_proc))
     t0 = time.time()
     # The numpy temporaries of _mean_pixel_distance make this path memory/allocator bound, so
-    # "all hardware threads" is not always the fastest process count: probe a few counts on a
-    # short round and keep the best one for the timed steps (the CPU gets its best shot).
-    candidates = sorted({max(1, cores // d) for d in (1, 2, 4, 8)} | {min(cores, c) for c in (8, 12, 16, 24, 48)},
-                        reverse=True)
+    # "all hardware threads" is not always the fastest process count: probe a few counts and keep the
+    # best one for the timed steps (the CPU gets its best shot).
+    candidates = sorted({max(1, cores // d) for d in (1, 2, 4)} | {min(cores, c) for c in (16, 24, 32, 48)}, reverse=True)
     probe = {}
     for p in candidates:
-        probe[p] = p * 4 / _ref_run_pool(args.detector, p, 4, args.width, args.height, args.seed, 1)[0]
+        rounds = _ref_run_pool(args.detector, p, 16, args.width, args.height, args.seed, 3)
+        probe[p] = p * 16 / rounds[-1]
     n_proc = max(probe, key=probe.get)
-    sample = n_proc * per_core
-    rounds = _ref_run_pool(args.detector, n_proc, per_core, args.width, args.height, args.seed,
+    sample = n_proc * per_proc
+    rounds = _ref_run_pool(args.detector, n_proc, per_proc, args.width, args.height, args.seed,
                            args.warmup + args.steps)
     step_times = rounds[args.warmup:]
     ms = 1000.0 * float(np.mean(step_times))
     value = sample / (ms / 1000.0)
     import cv2
+    _feat, _mk, det_desc = None, None, {"content": "ContentDetector() defaults: weights (1,1,1,0), threshold 27",
+                                        "content_edges": "ContentDetector(weights=(1,1,1,1))",
+                                        "adaptive": "AdaptiveDetector(window_width=5, weights=(1,1,1,1)) [edge component on]",
+                                        "threshold": "ThresholdDetector()",
+                                        "histogram": "HistogramDetector(bins=256)"}[args.detector]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.detector} detector on synthetic {args.width}x{args.height} BGR24 frames "
-                               f"(seed {args.seed}); bounded sample of {sample} frames per step",
-                   "parallelism": f"{n_proc} processes (best of {candidates} probed; host has {cores} hardware threads) "
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_text(det_desc, args.frames, args.width, args.height, args.seed,
+                                             (args.width, args.height)),
+                   "sample": f"bounded sample of {sample} frames per step ({per_proc} per process) of that sequence",
+                   "parallelism": f"{n_proc} processes (best of {candidates} in a warm probe; host has {cores} hardware threads) "
                                   "x contiguous time shards with 1-frame halo, cv2.setNumThreads(1)",
-                   "probe_frames_per_s": {str(k): round(v, 1) for k, v in probe.items()}},
+                   "probe_frames_per_s": {str(k): round(v, 1) for k, v in probe.items()},
+                   "step_frames_per_s": {"min": round(sample / max(step_times), 1),
+                                         "median": round(sample / float(np.median(step_times)), 1),
+                                         "max": round(sample / min(step_times), 1)}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_proc, "kind": "port",
-                         "sample": f"{sample} frames/step ({per_core} per process) of the same synthetic 1080p sequence; "
+                         "sample": f"{sample} frames/step ({per_proc} per process) of the same synthetic sequence; "
                                    f"oracle.ref_detectors = the reference's cv2 {cv2.__version__}/numpy {np.__version__} calls"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_text(det_desc, frames_per_gpu, w, h, seed, scored) -> str:
+    """Same wording in both arms (the driver compares the `config.workload` strings)."""
+    return (f"{det_desc} on {frames_per_gpu} synthetic {w}x{h} BGR24 frames per GPU (BASELINE.json configs[1]), "
+            f"seed {seed}, " + ("full resolution" if tuple(scored) == (w, h) else f"auto-downscaled on the device to {scored[0]}x{scored[1]}"))
+
+
+def ncu_traffic_per_frame() -> tuple[float | None, str]:
+    """dram bytes per 1080p frame of the fused HSV pass from the committed ncu summary (a citation, not a
+    measurement of this run): newest profiles/r*_ncu_score_ws_kernel*.txt that holds the counters."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_score_ws_kernel*.txt")), reverse=True):
+        try:
+            text = open(path).read()
+            rd = re.search(r"dram__bytes_read\.sum\s+(\w+)\s+([0-9.]+)", text)
+            wr = re.search(r"dram__bytes_write\.sum\s+(\w+)\s+([0-9.]+)", text)
+            fr = re.search(r"(\d+) frames 1920x1080", text)
+            if not (rd and wr and fr):
+                continue
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            total = float(rd.group(2)) * unit[rd.group(1)] + float(wr.group(2)) * unit[wr.group(1)]
+            return total / int(fr.group(1)), os.path.relpath(path, ROOT)
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, "no ncu summary with dram counters under profiles/"
 
 
 # ------------------------------------------------------------------------------------------
@@ -270,12 +319,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     lib = _capi.load()
 
-    W, H, N = args.width, args.height, args.frames
+    W, H = args.width, args.height
     fbytes = W * H * 3
     features, make_det, det_desc = detector_setup(args.detector)
-    total_frames = N * world
+    if args.scaling == "strong":
+        # fixed job: --frames in total, contiguous near-equal time shards (sharding.shard_bounds)
+        from pyscenedetect_b200.sharding import shard_bounds
+        total_frames = args.frames
+        bounds = shard_bounds(total_frames, world)
+        first, N = bounds[rank], bounds[rank + 1] - bounds[rank]
+    else:
+        N = args.frames
+        total_frames = N * world
+        first = rank * N
     plan = ScenePlan(total_frames, seed=args.seed)
-    first = rank * N
 
     # ---- resident input: this rank's contiguous time range, generated on the device ----
     frames_t = torch.empty(N * fbytes, dtype=torch.uint8, device=f"cuda:{dev}")
@@ -291,15 +348,19 @@ def run_ours(args):
         sw, sh = (max(1, round(W / f)), max(1, round(H / f))) if f > 1.0 else (W, H)
         max_batch = min(max_batch, 1024)
     eng = Engine(W, H, features, width=sw, height=sh, device=dev, max_batch=max_batch)
-    weights = (1.0, 1.0, 1.0, 1.0 if args.detector == "content_edges" else 0.0)
+    weights = (1.0, 1.0, 1.0, 1.0 if args.detector in ("content_edges", "adaptive") else 0.0)
     sums_ptr = None
     n_scan = N
     d_val = torch.empty(N, dtype=torch.float64, device=f"cuda:{dev}")
     d_comp = torch.empty(N * 4, dtype=torch.float64, device=f"cuda:{dev}")
     d_flag = torch.empty(N, dtype=torch.uint8, device=f"cuda:{dev}")
+    d_ratio = torch.empty(N, dtype=torch.float64, device=f"cuda:{dev}") if args.detector == "adaptive" else None
     wsum = float(sum(abs(x) for x in weights))
     import ctypes as C
     warr = (C.c_double * 4)(*weights)
+
+    ext_stream = torch.cuda.ExternalStream(eng.compute_stream, device=f"cuda:{dev}")
+    halo_ready = torch.cuda.Event()
 
     def barrier():
         if world > 1:
@@ -319,24 +380,27 @@ def run_ours(args):
                 ops.append(dist.P2POp(dist.irecv, halo_t, rank - 1))
             if ops:
                 for r in dist.batch_isend_irecv(ops):
-                    r.wait()
+                    r.wait()  # stream-level: torch's current stream waits for the NCCL transfer, the host does not
             if rank > 0:
-                torch.cuda.current_stream().synchronize()
+                halo_ready.record(torch.cuda.current_stream())
+                ext_stream.wait_event(halo_ready)  # the engine's compute stream picks the halo up when it has landed
                 eng.set_halo_device(halo_t.data_ptr())
         eng.submit_device(frames_t.data_ptr(), N, fbytes)
         sp, hp = eng.device_results()
         st = eng.compute_stream  # scans are ordered after the score kernel on the engine's stream
-        if args.detector in ("content", "content_edges"):
+        if args.detector in ("content", "content_edges", "adaptive"):
             _capi.check(lib.psd_scan_content(sp, N, sw * sh, warr, wsum, d_comp.data_ptr(), d_val.data_ptr(), st))
-            _capi.check(lib.psd_scan_compare(d_val.data_ptr(), N, 27.0, 0, d_flag.data_ptr(), st))
+            if args.detector == "adaptive":
+                # the rolling adaptive window as a trailing device scan (adaptive_detector.py:100-143)
+                _capi.check(lib.psd_scan_adaptive(d_val.data_ptr(), N, 5, 15.0, d_ratio.data_ptr(), st))
+            else:
+                _capi.check(lib.psd_scan_compare(d_val.data_ptr(), N, 27.0, 0, d_flag.data_ptr(), st))
         elif args.detector == "threshold":
             _capi.check(lib.psd_scan_average(sp, N, sw * sh * 3, d_val.data_ptr(), st))
         else:
             # the halo frame's histogram sits in the slot before stream frame 0 (psd_b200.h results layout)
             prev_hist = (hp - 256 * 4) if (world > 1 and rank > 0) else None
             _capi.check(lib.psd_scan_hist_correl(hp, N, 256, prev_hist, d_val.data_ptr(), st))
-
-    ext_stream = torch.cuda.ExternalStream(eng.compute_stream, device=f"cuda:{dev}")
 
     def step_synced():
         one_step()
@@ -380,19 +444,86 @@ def run_ours(args):
     # correctness spot check of what was timed (rank 0): cuts == ground-truth cuts of the plan
     flags = d_flag.cpu().numpy() if args.detector.startswith("content") else None
 
+    # ---- parity of what was timed: the device metric of this rank's first frames against the oracle, and at
+    #      N > 1 the shard boundary (frame `first` scored against the neighbour's last frame = the halo) ----
+    parity = None
+    if args.parity_frames != 0:
+        want_n = args.parity_frames if args.parity_frames else (48 if args.no_cpu else args.cpu_sample)
+        n_par = max(2, min(want_n, N)) if rank == 0 else 1
+        n_dl = n_par
+        sample = np.empty((n_dl, H, W, 3), dtype=np.uint8)
+        _capi.check(lib.psd_memcpy_d2h(dev, sample.ctypes.data, frames_t.data_ptr(), n_dl * fbytes))
+        det = ref_detector(args.detector)
+        t_lo = first
+        if rank > 0:
+            halo_host = np.empty((H, W, 3), dtype=np.uint8)
+            _capi.check(lib.psd_memcpy_d2h(dev, halo_host.ctypes.data, halo_t.data_ptr(), fbytes))
+            det.process_frame(first - 1, halo_host)
+        t_cpu0 = time.perf_counter()
+        oracle_vals, oracle_cuts = [], []
+        for i in range(n_dl):
+            oracle_cuts += det.process_frame(t_lo + i, sample[i])
+            if args.detector == "threshold":
+                oracle_vals.append(float(np.mean(sample[i])))
+            elif args.detector == "histogram":
+                oracle_vals.append(None)
+            else:
+                oracle_vals.append(float(det._frame_score))
+        cpu_dt = time.perf_counter() - t_cpu0
+        dev_vals = d_val[:n_dl].cpu().numpy()
+        if args.detector == "histogram":
+            # cv2.compareHist on the oracle side; BASELINE tolerance 1e-4 (the device sums in a different order)
+            h_det = ref_detector(args.detector)
+            h_det.with_stats = True
+            if rank > 0:
+                h_det.process_frame(first - 1, halo_host)
+            for i in range(n_dl):
+                h_det.process_frame(t_lo + i, sample[i])
+            pairs = [(h_det.metrics[t_lo + i][h_det.metric_key], dev_vals[i]) for i in range(n_dl) if (t_lo + i) in h_det.metrics]
+            ok = all(abs(a - b) < 1e-4 for a, b in pairs)
+            max_err = max([abs(a - b) for a, b in pairs], default=0.0)
+        else:
+            skip0 = 1 if (rank == 0 and args.detector != "threshold") else 0  # frame 0 has no predecessor: no score
+            ok = all(float(dev_vals[i]) == oracle_vals[i] for i in range(skip0, n_dl))
+            max_err = max([abs(float(dev_vals[i]) - oracle_vals[i]) for i in range(skip0, n_dl)], default=0.0)
+        cuts_ok = None
+        if rank == 0 and args.detector in ("content", "content_edges"):
+            # FlashFilter over the device flags of the same frames == the oracle's cuts among them
+            from oracle.ref_detectors import RefFlashFilter, _as_rate
+            ff = RefFlashFilter(RefFlashFilter.MERGE, 15, _as_rate(30.0))
+            dev_cuts = []
+            for i in range(n_dl):
+                dev_cuts += ff.filter(i, bool(flags[i]) and i > 0)
+            cuts_ok = dev_cuts == oracle_cuts
+        mine = torch.tensor([1.0 if ok else 0.0, max_err, 1.0 if cuts_ok in (None, True) else 0.0], dtype=torch.float64,
+                            device=f"cuda:{dev}")
+        allp = [torch.zeros_like(mine) for _ in range(world)] if world > 1 else [mine]
+        if world > 1:
+            dist.all_gather(allp, mine)
+        if rank == 0:
+            parity = {"frames": int(n_par), "bit_equal": bool(allp[0][0] > 0.5) if args.detector != "histogram" else None,
+                      "within_1e-4": bool(allp[0][0] > 0.5), "max_abs_err": float(max(float(x[1]) for x in allp)),
+                      "cuts_equal": (bool(allp[0][2] > 0.5) if cuts_ok is not None else None),
+                      "metric": {"threshold": "average_rgb", "histogram": "hist_diff"}.get(args.detector, "content_val"),
+                      "oracle": "oracle.ref_detectors on the same frames (downloaded from HBM after the timed steps)"}
+            if world > 1:
+                parity["shard_boundaries_checked"] = world - 1
+                parity["shard_boundaries_equal"] = all(bool(x[0] > 0.5) for x in allp[1:])
+            parity["_cpu_fps"] = n_dl / cpu_dt if cpu_dt > 0 else None
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         alg_bytes = fbytes * N * args.steps  # per-rank algorithmic bytes through the score kernel
         achieved = alg_bytes / (score_ms_total / 1000.0) / 1e9
+        traffic_pf, traffic_src = ncu_traffic_per_frame()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ev_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ev_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"{det_desc} on {N} synthetic {W}x{H} BGR24 frames per GPU "
-                            f"(BASELINE.json configs[1]), seed {args.seed}, "
-                            + ("full resolution" if (sw, sh) == (W, H) else f"auto-downscaled on the device to {sw}x{sh}"),
+                "workload": workload_text(det_desc, args.frames if args.scaling == "weak" else f"{total_frames} (total, split over {world})",
+                                          W, H, args.seed, (sw, sh)),
                 "frames_per_gpu": N, "total_frames": total_frames,
                 "parallelism": f"{world} contiguous time shards, 1-frame halo over NCCL p2p" if world > 1 else "single GPU",
                 "l2": f"inputs are {N * fbytes / 1e9:.1f} GB per step per GPU, larger than L2 (126 MB): no flush needed",
@@ -407,15 +538,16 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": fbytes,
                 "launches": int(score_launches), "avg_launch_ms": score_ms_total / max(1, score_launches),
-                # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to the
-                # average launch of this run (profiles/r01z_ncu_score_ws_kernel_final.txt: 6 470 488 272 B
-                # for a 1024-frame 1080p launch = 1.016x the algorithmic bytes)
-                "traffic": ((6470488272.0 / 1024.0) * (N * args.steps / max(1, score_launches)) / 1e9
-                            if (args.detector == "content" and (W, H) == (1920, 1080) and (sw, sh) == (W, H)) else None),
-                "traffic_unit": "GB per launch (ncu dram bytes, profiles/r01z_ncu_score_ws_kernel_final.txt)",
+                # dram__bytes_read+write of one `ncu --set full` capture of this kernel (a citation from the
+                # committed summary, NOT measured in this run), scaled to the average launch of this run
+                "traffic": (traffic_pf * (N * args.steps / max(1, score_launches)) / 1e9
+                            if (traffic_pf and args.detector == "content" and (W, H) == (1920, 1080) and (sw, sh) == (W, H)) else None),
+                "traffic_unit": f"GB per launch, cited from {traffic_src} (one ncu capture, scaled by frames per launch; not measured in this run)",
                 "achieved_bytes_per_launch_gb": fbytes * N * args.steps / max(1, score_launches) / 1e9,
             },
         }
+        if parity is not None:
+            line["parity_check"] = {k: v for k, v in parity.items() if not k.startswith("_")}
         if flags is not None:
             line["config"]["frames_above_threshold"] = int(flags.sum())
         if world == 1 and args.detector == "content" and (sw, sh) == (W, H):
@@ -445,7 +577,7 @@ def run_ours(args):
             from pyscenedetect_b200.sharding import TorchComm, detect_sharded
             comm = TorchComm(device=torch.device("cuda", dev))
             cuts, _sums = detect_sharded(host_frames, first, total_frames, make_det(), 30.0, comm,
-                                         batch_size=64, n_local=N, pinned=True, device=dev)
+                                         batch_size=64, n_local=N, pinned=True, device=dev, timings=e2e_phases)
             return N, (len(cuts) if cuts is not None else 0)
 
         def e2e_step_single():
@@ -458,6 +590,7 @@ def run_ours(args):
             return n, len(cuts)
 
         e2e_step = e2e_step_sharded if world > 1 else e2e_step_single
+        e2e_phases: dict = {}
 
         for _ in range(min(args.warmup, 1)):
             e2e_step()
@@ -481,6 +614,8 @@ def run_ours(args):
                 "cuts_found": n_cuts,
                 "host_numa": numa,
             }
+            if e2e_phases:  # rank 0's last step: halo exchange, H2D + fused pass, result gather, scans + cut automata
+                line["e2e"]["breakdown"] = {k.replace("_s", "_ms"): round(1000.0 * v, 2) for k, v in e2e_phases.items()}
         pin.close()
         os.sched_setaffinity(0, orig_affinity)
 

@@ -130,3 +130,25 @@ class DeviceCuts:
                                            1 if add_final_scene else 0, self._cuts.ptr, self._count.ptr,
                                            self._cap, self._stream), "psd_cuts_threshold")
         return self._fetch()
+
+
+def cuts_for_detector(dc: DeviceCuts, detector, fps, first_frame: int = 0) -> list[int]:
+    """Run the device automaton that corresponds to a (fresh) detector object of this package with the
+    detector's own parameters: the cut list its per-frame `process_frame` + `post_process` would produce."""
+    from .compat import FlashFilter
+    from .detectors import AdaptiveDetector, ContentDetector, HistogramDetector, ThresholdDetector
+    if isinstance(detector, AdaptiveDetector):
+        return dc.adaptive(tuple(detector._weights), detector.adaptive_threshold, detector.min_scene_len,
+                           detector.window_width, detector.min_content_val, fps, first_frame)
+    if isinstance(detector, ContentDetector):
+        ff = detector._flash_filter
+        length = ff._filter_secs if ff._filter_secs is not None else ff._filter_length
+        return dc.content(tuple(detector._weights), detector._threshold, length, fps,
+                          suppress=ff._mode == FlashFilter.Mode.SUPPRESS, first_frame=first_frame)
+    if isinstance(detector, HistogramDetector):
+        # the constructor stored 1 - threshold (clamped); DeviceCuts.histogram applies the same map
+        return dc.histogram(1.0 - detector._threshold, detector._bins, detector._min_scene_len, fps, first_frame)
+    if isinstance(detector, ThresholdDetector):
+        return dc.threshold(detector.threshold, detector.min_scene_len, detector.fade_bias, detector.add_final_scene,
+                            detector.method == ThresholdDetector.Method.CEILING, fps, first_frame)
+    raise TypeError(f"no device automaton for {type(detector).__name__}")

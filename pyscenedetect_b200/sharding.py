@@ -53,25 +53,31 @@ class TorchComm:
         if recv is None:
             return None
         if recv.is_cuda:
-            torch.cuda.synchronize()
+            # the halo stays in HBM: the engine copies it device-to-device (psd_engine_set_halo_device)
+            torch.cuda.current_stream().synchronize()
+            self._halo_keepalive = recv
+            return recv
         return recv.cpu().numpy()
 
     def gather_rows(self, rows: np.ndarray, counts: list[int]) -> np.ndarray | None:
-        """Concatenate per-rank row blocks (raw bytes) on rank 0; other ranks get None."""
+        """Concatenate per-rank row blocks (raw bytes) on rank 0; other ranks get None.  One `gather`
+        (only rank 0 receives), blocks padded to the longest shard (shards differ by at most one row)."""
         dist, torch = self.dist, self.torch
+        if self.world == 1:
+            return rows
         row_bytes = rows.dtype.itemsize * int(np.prod(rows.shape[1:], dtype=np.int64))
         cap = max(counts) * row_bytes
-        buf = torch.zeros(cap, dtype=torch.uint8, device=self.device)
-        raw = np.frombuffer(np.ascontiguousarray(rows).tobytes(), dtype=np.uint8)
-        buf[: raw.size] = self._t(raw)
-        outs = [torch.empty_like(buf) for _ in range(self.world)]
-        dist.all_gather(outs, buf)
+        raw = np.zeros(cap, dtype=np.uint8)
+        flat = np.ascontiguousarray(rows).view(np.uint8).reshape(-1)
+        raw[: flat.size] = flat
+        buf = torch.from_numpy(raw).to(self.device)
+        outs = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(buf, outs, dst=0)
         if self.rank != 0:
             return None
-        parts = []
-        for r, o in enumerate(outs):
-            b = o[: counts[r] * row_bytes].cpu().numpy().tobytes()
-            parts.append(np.frombuffer(b, dtype=rows.dtype).reshape((counts[r],) + rows.shape[1:]))
+        host = torch.stack(outs).cpu().numpy()  # one device->host copy of all blocks
+        parts = [np.frombuffer(host[r, : counts[r] * row_bytes].tobytes(), dtype=rows.dtype)
+                 .reshape((counts[r],) + rows.shape[1:]) for r in range(self.world)]
         return np.concatenate(parts)
 
 
@@ -100,6 +106,15 @@ class GatheredResults:
     @property
     def frame_count(self) -> int:
         return self._n
+
+    # the part of the `Engine` interface `device_cuts.DeviceCuts` needs: the gathered arrays live in HBM
+    compute_stream = 0  # scans and automata run on the default stream, the downloads below are stream-ordered
+
+    def device_results(self):
+        return self._sums.ptr, (self._hist.ptr if self._hist is not None else None)
+
+    def sync(self):
+        pass
 
     def _out(self, count: int):
         return self._DeviceBuffer(max(8, count * 8), self.device)
@@ -143,7 +158,8 @@ class GatheredResults:
 
 def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int, detector, fps,
                    comm, engine_factory=None, results_factory=None, batch_size: int = 64,
-                   n_local: int | None = None, pinned: bool = False, device: int = 0):
+                   n_local: int | None = None, pinned: bool = False, device: int = 0,
+                   timings: dict | None = None):
     """Run `detector` over a sequence that is split across ranks by contiguous time range.
 
     frames_local: this rank's frames (n_local,H,W,3) = global frames [first_index, first_index+n_local).
@@ -152,8 +168,17 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
     Returns (cut_frame_numbers, gathered_sums) on rank 0 and (None, None) elsewhere.
     `engine_factory` / `results_factory` exist so the CPU tests can substitute oracle-backed
     scorers; the defaults are the CUDA engine and the C-ABI device scans.
+
+    On rank 0 the cut list comes from the device automata (`device_cuts.DeviceCuts`: psd_scan_* +
+    psd_cuts_* over the gathered arrays, only the cut frame numbers travel back) unless the detector
+    carries a StatsManager - then the per-frame Python state machines run so that every metric row
+    is recorded.  `timings`, if given, receives the wall seconds of the phases (halo, score incl. H2D,
+    gather, cuts).
     """
+    import time
+
     from .compat import FrameTimecode
+    t_start = time.perf_counter()
     if engine_factory is None:
         from .engine import Engine as engine_factory  # noqa: N813
     if results_factory is None:
@@ -165,7 +190,11 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
                          edge_kernel_size=detector.edge_kernel_size_arg())
     halo = comm.exchange_halo(frames_local[(n_local - 1) % ring] if n_local else None, (h, w, 3))
     if halo is not None:
-        eng.set_halo(halo)
+        if isinstance(halo, np.ndarray):
+            eng.set_halo(halo)
+        else:
+            eng.set_halo_device(halo.data_ptr())
+    t_halo = time.perf_counter()
     i = 0
     while i < n_local:
         j = i % ring
@@ -174,16 +203,29 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
         i += k
     sums = eng.read_sums()
     yh = eng.read_yhist() if features & F_YHIST else None
+    t_score = time.perf_counter()
     counts = [b - a for a, b in zip(shard_bounds(total_frames, comm.world)[:-1],
                                     shard_bounds(total_frames, comm.world)[1:])]
     assert counts[comm.rank] == n_local and shard_bounds(total_frames, comm.world)[comm.rank] == first_index
     all_sums = comm.gather_rows(sums, counts)
     all_hist = comm.gather_rows(yh, counts) if yh is not None else None
     eng.close()
+    t_gather = time.perf_counter()
+
+    def note(t_end):
+        if timings is not None:
+            timings.update(halo_s=t_halo - t_start, score_s=t_score - t_halo, gather_s=t_gather - t_score,
+                           cuts_s=t_end - t_gather)
     if comm.rank != 0:
+        note(t_gather)
         return None, None
     assert all_sums.dtype == SUMS_DTYPE and all_sums.shape[0] == total_frames
     res = results_factory(all_sums, all_hist, w * h, device)
+    if detector.stats_manager is None and hasattr(res, "device_results"):
+        from .device_cuts import DeviceCuts, cuts_for_detector
+        cut_frames = sorted(set(cuts_for_detector(DeviceCuts(res), detector, fps)))
+        note(time.perf_counter())
+        return cut_frames, all_sums
     detector.attach_engine(res)
     detector._base_index = 0
     tcs = [FrameTimecode(i, fps) for i in range(total_frames)]
@@ -191,4 +233,5 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
     for i in range(0, total_frames, 4096):
         cuts += detector.consume_results(tcs[i:i + 4096], i)
     cuts += detector.post_process(tcs[-1])
+    note(time.perf_counter())
     return sorted({c.frame_num for c in cuts}), all_sums

@@ -478,6 +478,28 @@ def test_device_cut_state_machines_match_golden(lib, name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", case_names())
+def test_gathered_results_device_automata_match_golden(lib, name):
+    """The rank-0 tail of sharding.detect_sharded: integer results uploaded as one array
+    (`GatheredResults`), then scans + cut automata on the device with the DETECTOR OBJECT's own parameters
+    (`cuts_for_detector`) - no per-frame Python."""
+    from pyscenedetect_b200.device_cuts import DeviceCuts, cuts_for_detector
+    from pyscenedetect_b200.engine import F_YHIST, Engine
+    from pyscenedetect_b200.sharding import GatheredResults
+    case = get_case(name)
+    frames = case_frames(case)
+    det = _build(case)
+    size = _scored_size(case) or (frames.shape[2], frames.shape[1])
+    eng = Engine(frames.shape[2], frames.shape[1], det.required_features(), width=size[0], height=size[1],
+                 max_batch=64, edge_kernel_size=det.edge_kernel_size_arg())
+    eng.submit(frames)
+    sums = eng.read_sums()
+    hist = eng.read_yhist() if det.required_features() & F_YHIST else None
+    eng.close()
+    res = GatheredResults(sums, hist, size[0] * size[1])
+    assert sorted(set(cuts_for_detector(DeviceCuts(res), det, case["fps"]))) == case["cuts"]
+
+
 def test_independent_engines_in_threads(lib):
     """SURVEY §8b threading contract: engines are single-producer but independent engines may run
     concurrently (benchmark sweeps use one SceneManager per thread)."""
