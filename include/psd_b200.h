@@ -39,6 +39,10 @@ extern "C" {
 #define PSD_F_YHIST 4u  /* 256-bin histogram of YUV-Y: histogram_detector.py:156-159 */
 #define PSD_F_EDGES 8u  /* Canny+dilate edge-map SAD: content_detector.py:213-239 (implies HSV) */
 
+/* engine flags (psd_config.flags) */
+#define PSD_CFG_GENERIC_KERNEL 1u /* score every strip with the generic kernel instead of the persistent
+                                     warp-specialised one (same results; exists so tests can cross-check the two) */
+
 /* submit flags */
 #define PSD_SUBMIT_PINNED 1u /* host buffer is page-locked (psd_host_alloc): DMA straight from it,
                                 caller keeps it unchanged until psd_engine_sync() */
@@ -56,7 +60,8 @@ typedef struct psd_config {
     uint32_t features;        /* PSD_F_* */
     int32_t edge_kernel_size; /* dilate kernel k (odd >= 3); 0 = content_detector.py:39-46 estimate */
     int32_t max_batch;        /* max frames per submit call (staging is sized for it) */
-    int32_t reserved[7];
+    uint32_t flags;           /* PSD_CFG_* */
+    int32_t reserved[6];
 } psd_config;
 
 /* Per-frame integer results (device- and host-side layout, 64 bytes). */
@@ -188,7 +193,8 @@ int psd_synth_frames(int device, void* d_out, const int32_t* params_host, int64_
                      int32_t height, int64_t frame_stride, void* stream);
 
 /* ---- test hooks ---- */
-/* device BGR (n pixels) -> H,S,V planes with the same device function the fused kernel uses */
+/* device BGR (n pixels) -> H,S,V planes with the device functions the fused pass uses:
+ * variant 7 = the warp-specialised kernel's arithmetic, 2 = the generic kernel's */
 int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixels, uint8_t* h_out, uint8_t* s_out,
                  uint8_t* v_out, uint8_t* y_out, int variant);
 

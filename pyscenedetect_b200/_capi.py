@@ -26,6 +26,7 @@ F_BGRSUM = 2
 F_YHIST = 4
 F_EDGES = 8
 SUBMIT_PINNED = 1
+CFG_GENERIC_KERNEL = 1
 
 
 class PsdConfig(C.Structure):
@@ -39,7 +40,8 @@ class PsdConfig(C.Structure):
         ("features", C.c_uint32),
         ("edge_kernel_size", C.c_int32),
         ("max_batch", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("flags", C.c_uint32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

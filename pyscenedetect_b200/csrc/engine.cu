@@ -53,7 +53,7 @@ struct psd_engine {
     uint32_t features = 0;
     int ksize = 0;
     int max_batch = 0;
-    int variant = 1;
+    bool generic_only = false;  // PSD_CFG_GENERIC_KERNEL: score with the generic kernel only (cross-check)
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     // staging (double buffered)
     uint8_t* pinned[2] = {nullptr, nullptr};
@@ -159,7 +159,7 @@ static int run_batch(psd_engine* e, const uint8_t* src, int64_t src_frame_stride
     a.vhist = (e->features & PSD_F_EDGES) ? e->eb.vhist : nullptr;
     a.vplane = (e->features & PSD_F_EDGES) ? e->eb.vplane : nullptr;
     PSD_CUDA(cudaEventRecord(k0, st));
-    int rc = launch_score(a, e->features, e->variant, st);
+    int rc = launch_score(a, e->features, e->generic_only, st);
     if (rc) return rc;
     PSD_CUDA(cudaEventRecord(k1, st));
     e->ev_score.push_back({k0, k1});
@@ -254,10 +254,9 @@ void psd_engine_destroy(psd_engine* e) {
     }
     cudaFree(e->small); cudaFree(e->d_xofs); cudaFree(e->d_xa); cudaFree(e->d_yofs); cudaFree(e->d_ya);
     cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist);
-    cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.map);
+    cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.cand);
     cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
-    cudaFree(e->eb.carry_bits); cudaFree(e->eb.changed); cudaFree(e->eb.dirty); cudaFree(e->eb.labels); cudaFree(e->eb.tile_rec);
-    if (e->eb.changed_host) cudaFreeHost(e->eb.changed_host);
+    cudaFree(e->eb.carry_bits); cudaFree(e->eb.dirty); cudaFree(e->eb.hyst_flags);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
@@ -311,8 +310,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
     e->src_frame_bytes = (int64_t)e->sw * e->sh * 3;
     e->features = cfg->features | ((cfg->features & PSD_F_EDGES) ? PSD_F_HSV : 0);
     e->max_batch = cfg->max_batch;
-    e->variant = 7;  // warp-specialised kernel with the pixel-pair HSV arithmetic + generic remainder (score_kernel.cu)
-    if (const char* v = getenv("PSD_HSV_VARIANT")) e->variant = atoi(v);
+    e->generic_only = (cfg->flags & PSD_CFG_GENERIC_KERNEL) != 0;
     if (e->features & PSD_F_EDGES) {
         int k = cfg->edge_kernel_size;
         if (k == 0) {  // content_detector.py:39-46; Python round() is half-to-even like nearbyint
@@ -343,10 +341,8 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
     if (e->features & PSD_F_EDGES) {
         const size_t plane = (size_t)e->P * e->max_batch;
         ENG_CUDA(cudaMalloc(&e->eb.vplane, plane));
-        ENG_CUDA(cudaMalloc(&e->eb.map, plane));
-        ENG_CUDA(cudaMalloc(&e->eb.labels, plane * sizeof(int32_t)));
-        ENG_CUDA(cudaMalloc(&e->eb.tile_rec, (size_t)e->max_batch * ((e->W + 63) / 64) * ((e->H + 31) / 32) * 16 * sizeof(int32_t)));
         const size_t words = (size_t)e->H * ((e->W + 31) / 32);
+        ENG_CUDA(cudaMalloc(&e->eb.cand, words * 4 * e->max_batch));
         ENG_CUDA(cudaMalloc(&e->eb.tmp, (size_t)e->P));
         ENG_CUDA(cudaMalloc(&e->eb.bits_in, words * 4 * e->max_batch));
         ENG_CUDA(cudaMalloc(&e->eb.bits_row, words * 4 * e->max_batch));
@@ -354,9 +350,8 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         ENG_CUDA(cudaMalloc(&e->eb.carry_bits, words * 4));
         ENG_CUDA(cudaMalloc(&e->eb.vhist, (size_t)e->max_batch * 256 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.thresholds, (size_t)e->max_batch * 2 * 4));
-        ENG_CUDA(cudaMalloc(&e->eb.changed, 64));
-        ENG_CUDA(cudaMalloc(&e->eb.dirty, (size_t)2 * e->max_batch * ((e->W + 31) / 32) * ((e->H + 31) / 32)));
-        ENG_CUDA(cudaHostAlloc((void**)&e->eb.changed_host, 4, cudaHostAllocDefault));
+        ENG_CUDA(cudaMalloc(&e->eb.hyst_flags, 64));
+        ENG_CUDA(cudaMalloc(&e->eb.dirty, (size_t)2 * e->max_batch * ((e->W + 63) / 64) * ((e->H + 31) / 32)));
     }
     {
         int rc = ensure_capacity(e, 4096);
@@ -564,11 +559,6 @@ int psd_engine_timing_ms(psd_engine* e, float* total_ms, float* score_ms, uint64
     return PSD_OK;
 }
 
-__global__ void psd_map_to_255_kernel(const uint8_t* in, uint8_t* out, int64_t n) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (in[i] >= 2) ? 255 : 0;  // 2 = edge, 3 = edge that is a marked component root
-}
-
 int psd_engine_debug_plane(psd_engine* e, int which, int64_t index, uint8_t* out, size_t cap) {
     PSD_REQUIRE(e && out, "psd_engine_debug_plane: null argument");
     PSD_REQUIRE(index >= 0 && index < e->last_n, "index outside the last batch");
@@ -582,23 +572,16 @@ int psd_engine_debug_plane(psd_engine* e, int which, int64_t index, uint8_t* out
     PSD_REQUIRE(e->features & PSD_F_EDGES, "engine was created without PSD_F_EDGES");
     PSD_REQUIRE(cap >= (size_t)e->P, "buffer too small");
     PSD_REQUIRE(which >= 1 && which <= 3, "unknown plane %d", which);
-    if (which == 3) {
+    if (which == 2 || which == 3) {  // bit-packed maps -> 0/255 bytes
         const size_t words = (size_t)e->H * ((e->W + 31) / 32);
-        rc = edge_unpack(e->eb.bits_dil + index * words, e->eb.tmp, e->W, e->H, e->compute_stream);
+        const uint32_t* bits = (which == 3 ? e->eb.bits_dil : e->eb.bits_in) + index * words;
+        rc = edge_unpack(bits, e->eb.tmp, e->W, e->H, e->compute_stream);
         if (rc) return rc;
         PSD_CUDA(cudaStreamSynchronize(e->compute_stream));
         PSD_CUDA(cudaMemcpy(out, e->eb.tmp, (size_t)e->P, cudaMemcpyDeviceToHost));
         return PSD_OK;
     }
-    const uint8_t* src = which == 1 ? e->eb.vplane : e->eb.map;
-    if (which == 2) {
-        psd_map_to_255_kernel<<<(unsigned)((e->P + 255) / 256), 256, 0, e->compute_stream>>>(
-            src + index * e->P, e->eb.tmp, e->P);
-        PSD_CHECK_LAUNCH();
-        PSD_CUDA(cudaStreamSynchronize(e->compute_stream));
-        src = e->eb.tmp - index * e->P;
-    }
-    PSD_CUDA(cudaMemcpy(out, src + index * e->P, (size_t)e->P, cudaMemcpyDeviceToHost));
+    PSD_CUDA(cudaMemcpy(out, e->eb.vplane + index * e->P, (size_t)e->P, cudaMemcpyDeviceToHost));
     return PSD_OK;
 }
 

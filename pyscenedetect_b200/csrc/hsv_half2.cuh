@@ -1,8 +1,9 @@
-// Variant 7 of the exact OpenCV BGR->HSV arithmetic (see hsv_math.cuh for the formulas): the
-// numerator stage runs on pixel PAIRS in packed 16-bit lanes, so most instructions serve two pixels.
+// The exact OpenCV BGR->HSV arithmetic of the warp-specialised fused pass (see hsv_math.cuh for the
+// formulas): the numerator stage runs on pixel PAIRS in packed 16-bit lanes, so most instructions serve
+// two pixels.  ("variant 7" in DESIGN.md's history of formulations.)
 //
 // The fused pass is issue-bound (one warp instruction per clock per sub-partition), so the lever is
-// the instruction COUNT per pixel.  Variant 4 spends ~27.6; this one ~20:
+// the instruction COUNT per pixel; this formulation needs ~20:
 //   * bytes are lifted straight into half2 "magic" lanes 0x6400 | x = 1024 + x (ulp 1), 8 PRMT/LOP3
 //     per 4 pixels instead of 12 single-byte lifts;
 //   * V = max3, mn = min3 are ONE VIMNMX3.U16x2 each per pair (the magic bit patterns order like the
@@ -11,14 +12,15 @@
 //     HADD2/HFMA2 on pairs; the R > G > B tie priority becomes two HSET2 lane masks + two LOP3
 //     selects per pair;
 //   * only the two table products stay per pixel and in fp32: HADD2.F32 lifts a lane of d / h,
-//     yS = fma.rz(d, sdiv/4096, 32768.5), yH = fma.rm(h, hdiv/4096, 49152.5) exactly as in variant 4
-//     (byte 1 of the result = S resp. H mod 256), with each LUT row address built by one IDP2A
-//     (u16 lane x 128 + addend; PSD_V7_ADDR selects PRMT / IMAD.HI alternatives, measured equal);
+//     yS = fma.rz(d, sdiv/4096, 32768.5), yH = fma.rm(h, hdiv/4096, 49152.5): the FMA is exact before its
+//     single rounding, RZ / RM at ulp 2^-8 only drop fraction bits and the integer part lands in bits 8..15
+//     (byte 1 of the result = S resp. H mod 256); each LUT row address is built by one IDP2A
+//     (u16 lane x 128 + addend);
 //   * "H += 180 if H < 0" is applied after packing, on four pixels at once: H mod 256 is either
 //     0..179 or 226..255, so a byte is negative iff its bits 7 and 6 are both set, and adding 180
 //     mod 256 equals subtracting 76 without a borrow.
 // Every step is an exact integer identity; pinned over all 2^24 colours by tests/test_gpu_parity.py
-// (psd_test_hsv, variants 7 and 8) and restated in numpy by tests/v7_model.py, which
+// (psd_test_hsv, variant 7) and restated in numpy by tests/v7_model.py, which
 // tests/test_v7_model.py pins against the oracle over all 2^24 colours on the CPU.
 #pragma once
 
@@ -29,47 +31,21 @@
 
 namespace psd {
 
-// Row addressing of the per-lane replicated LUT, selectable at compile time (measured with
-// tools/microbench/hsv_rate.cu; the default is the fastest in the fused kernel):
-//   PSD_V7_ADDR 0: rows of 128 B in two tables (sdiv | hdiv); both lanes use IDP2A
-//                  (u16 lane x 128 + addend): fma half of the sub-partition
-//   PSD_V7_ADDR 1: rows of 256 B (sdiv column | hdiv column, the variant-4 layout); lane 0 uses PRMT
-//                  (alu half), lane 1 IMAD.HI (x >> 8, fma half; needs shift24 == 0x01000000 at run time,
-//                  which only the engine passes - tools/microbench/hsv_rate.cu cannot run this mode)
-//   PSD_V7_ADDR 2: 256 B rows, both lanes PRMT
-#ifndef PSD_V7_ADDR
-#define PSD_V7_ADDR 0
-#endif
-#ifndef PSD_V7_HMNMX
-#define PSD_V7_HMNMX 0  // 1: max3/min3 with VHMNMX (half2) instead of VIMNMX3.U16x2
-#endif
-// Template flag FMA2 (engine variant 8): the S and H products of a pixel share one fma.rm.f32x2
-// (S >= 0, so round-toward-zero equals round-down): one issue slot less per pixel.
-
+// The LUT is replicated per lane (32 copies of each of the 2 x 256 table values, 64 KB): rows of 128 B in two
+// tables (sdiv | hdiv), lane l reads word l of a row, so any 32 lookups hit 32 distinct banks.
 struct LutView7 {
-    uint32_t l0s;   // lane * 4            (byte 0; bytes 1..3 zero): PRMT operand, sdiv column
-    uint32_t l0h;   // lane * 4 + 128      ... hdiv column
-    uint32_t base;  // shared-window address of the LUT (warp-uniform)
-    uint32_t cs;    // addend of the sdiv row offset (meaning depends on PSD_V7_ADDR)
-    uint32_t ch;    // addend of the hdiv row offset
+    uint32_t cs;    // addend of the sdiv row address: (0x6400 + V) * 128 + cs = table + V * 128 + lane * 4
+    uint32_t ch;    // addend of the hdiv row address: d * 128 + ch
 };
 
 __device__ __forceinline__ LutView7 make_lut7(uint32_t lut_smem_addr, int lane) {
     LutView7 l;
-    l.l0s = (uint32_t)lane * 4u;
-    l.l0h = l.l0s + 128u;
-    l.base = lut_smem_addr;
-#if PSD_V7_ADDR == 0
-    l.cs = lut_smem_addr + l.l0s - 0x6400u * 128u;  // (0x6400 + V) * 128 + cs = V * 128 + lane * 4
-    l.ch = lut_smem_addr + 32768u + l.l0s;          // hdiv table follows the sdiv table
-#else
-    l.cs = lut_smem_addr + l.l0s - 0x00640064u;     // (Vh >> 8) + cs = V1 * 256 + lane * 4
-    l.ch = lut_smem_addr + l.l0h;
-#endif
+    l.cs = lut_smem_addr + (uint32_t)lane * 4u - 0x6400u * 128u;
+    l.ch = lut_smem_addr + 32768u + (uint32_t)lane * 4u;  // hdiv table follows the sdiv table
     return l;
 }
 
-// fills the LUT in the layout PSD_V7_ADDR selects: value = table integer / 4096 (exact in fp32)
+// fills the LUT: value = table integer / 4096 (exact in fp32: < 2^21 and a power-of-two divisor)
 __device__ __forceinline__ void lut_fill7(float* lut, int tid, int nthreads) {
     for (int t = tid; t < 512; t += nthreads) {
         const int row = t >> 1, which = t & 1;
@@ -79,11 +55,7 @@ __device__ __forceinline__ void lut_fill7(float* lut, int tid, int nthreads) {
                                 : __double2int_rn(1044480.0 / (double)row);
             v = (float)q * 0.000244140625f;
         }
-#if PSD_V7_ADDR == 0
         float4* dst = reinterpret_cast<float4*>(lut + which * 8192 + row * 32);
-#else
-        float4* dst = reinterpret_cast<float4*>(lut + row * 64 + which * 32);
-#endif
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v, v, v, v);
     }
@@ -111,11 +83,6 @@ __device__ __forceinline__ uint32_t even_bytes_magic(uint32_t t) {
     asm("lop3.b32 %0, %1, 0x00FF00FF, %2, 0xEA;" : "=r"(r) : "r"(t), "r"(0x64006400u));  // (a & b) | c
     return r;
 }
-__device__ __forceinline__ uint32_t mulhi_add(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
 __device__ __forceinline__ float lds(uint32_t addr) {
     float r;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
@@ -137,18 +104,10 @@ struct PairOut7 {
     uint32_t vh;                  // half2 magic lanes: byte 0 = V of lane 0, byte 2 = V of lane 1
 };
 
-// Bh, Gh, Rh: magic half2 lanes of one pixel pair.  shift24 = 0x01000000 held in a register so the
-// lane-1 row address stays an IMAD.HI (fma half) instead of being strength-reduced to SHF + IADD.
-template <bool FMA2>
-__device__ __forceinline__ void pair(uint32_t Bh, uint32_t Gh, uint32_t Rh, const LutView7& lut,
-                                     uint32_t shift24, PairOut7& o) {
-#if PSD_V7_HMNMX
-    const uint32_t Vh = as_u32(__hmax2(__hmax2(as_h2(Bh), as_h2(Gh)), as_h2(Rh)));
-    const uint32_t mh = as_u32(__hmin2(__hmin2(as_h2(Bh), as_h2(Gh)), as_h2(Rh)));
-#else
+// Bh, Gh, Rh: magic half2 lanes of one pixel pair.
+__device__ __forceinline__ void pair(uint32_t Bh, uint32_t Gh, uint32_t Rh, const LutView7& lut, PairOut7& o) {
     const uint32_t Vh = __vimax3_u16x2(Bh, Gh, Rh);
     const uint32_t mh = __vimin3_u16x2(Bh, Gh, Rh);
-#endif
     const uint32_t dh = hsub2u(Vh, mh);  // half2 d, exact
     const uint32_t di = Vh - mh;         // integer d per 16-bit lane (each lane >= 0: no borrow)
     const uint32_t hR = hsub2u(Gh, Bh);
@@ -160,33 +119,12 @@ __device__ __forceinline__ void pair(uint32_t Bh, uint32_t Gh, uint32_t Rh, cons
     // per-lane table products
     const float d0 = __low2float(as_h2(dh)), d1 = __high2float(as_h2(dh));
     const float h0 = __low2float(as_h2(hh)), h1 = __high2float(as_h2(hh));
-#if PSD_V7_ADDR == 0
     const uint32_t aS0 = __dp2a_lo(Vh, 0x00000080u, lut.cs), aS1 = __dp2a_lo(Vh, 0x00008000u, lut.cs);
     const uint32_t aH0 = __dp2a_lo(di, 0x00000080u, lut.ch), aH1 = __dp2a_lo(di, 0x00008000u, lut.ch);
-#elif PSD_V7_ADDR == 1
-    const uint32_t aS0 = __byte_perm(Vh, lut.l0s, 0x6504) + lut.base;  // V0 * 256 + lane * 4 (+ base)
-    const uint32_t aH0 = __byte_perm(di, lut.l0h, 0x6504) + lut.base;  // d0 * 256 + lane * 4 + 128
-    const uint32_t aS1 = mulhi_add(Vh, shift24, lut.cs);               // (Vh >> 8) - 0x640064 + ...
-    const uint32_t aH1 = mulhi_add(di, shift24, lut.ch);               // d1 * 256 + ...
-#else
-    const uint32_t aS0 = __byte_perm(Vh, lut.l0s, 0x6504) + lut.base;
-    const uint32_t aH0 = __byte_perm(di, lut.l0h, 0x6504) + lut.base;
-    const uint32_t aS1 = __byte_perm(Vh, lut.l0s, 0x6524) + lut.base;
-    const uint32_t aH1 = __byte_perm(di, lut.l0h, 0x6524) + lut.base;
-#endif
-    if (FMA2) {
-        const f32x2_t magic = pack2(32768.5f, 49152.5f);
-        float s0, s1, g0, g1;
-        unpack2(fma2_rm(pack2(d0, h0), pack2(lds(aS0), lds(aH0)), magic), s0, g0);
-        unpack2(fma2_rm(pack2(d1, h1), pack2(lds(aS1), lds(aH1)), magic), s1, g1);
-        o.ys0 = __float_as_uint(s0); o.ys1 = __float_as_uint(s1);
-        o.yh0 = __float_as_uint(g0); o.yh1 = __float_as_uint(g1);
-    } else {
-        o.ys0 = __float_as_uint(fma_rz_(d0, lds(aS0), 32768.5f));
-        o.ys1 = __float_as_uint(fma_rz_(d1, lds(aS1), 32768.5f));
-        o.yh0 = __float_as_uint(fma_rm_(h0, lds(aH0), 49152.5f));
-        o.yh1 = __float_as_uint(fma_rm_(h1, lds(aH1), 49152.5f));
-    }
+    o.ys0 = __float_as_uint(fma_rz_(d0, lds(aS0), 32768.5f));
+    o.ys1 = __float_as_uint(fma_rz_(d1, lds(aS1), 32768.5f));
+    o.yh0 = __float_as_uint(fma_rm_(h0, lds(aH0), 49152.5f));
+    o.yh1 = __float_as_uint(fma_rm_(h1, lds(aH1), 49152.5f));
     o.vh = Vh;
 }
 
@@ -199,9 +137,7 @@ __device__ __forceinline__ uint32_t fix_hue4(uint32_t hw) {
 
 }  // namespace v7
 
-template <bool FMA2>
-__device__ __forceinline__ void hsv16_v7(const uint32_t (&w)[12], Px16& o, const LutView7& lut,
-                                         uint32_t shift24) {
+__device__ __forceinline__ void hsv16_v7(const uint32_t (&w)[12], Px16& o, const LutView7& lut) {
     const uint32_t K = 0x64646464u;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -216,8 +152,8 @@ __device__ __forceinline__ void hsv16_v7(const uint32_t (&w)[12], Px16& o, const
         const uint32_t B23 = v7::even_bytes_magic(t23);
         const uint32_t G23 = __byte_perm(t23, K, 0x4341);
         v7::PairOut7 p, q;
-        v7::pair<FMA2>(B01, G01, R01, lut, shift24, p);
-        v7::pair<FMA2>(B23, G23, R23, lut, shift24, q);
+        v7::pair(B01, G01, R01, lut, p);
+        v7::pair(B23, G23, R23, lut, q);
         const uint32_t hw = __byte_perm(__byte_perm(p.yh0, p.yh1, 0x0051), __byte_perm(q.yh0, q.yh1, 0x0051), 0x5410);
         o.h[g] = v7::fix_hue4(hw);
         o.s[g] = __byte_perm(__byte_perm(p.ys0, p.ys1, 0x0051), __byte_perm(q.ys0, q.ys1, 0x0051), 0x5410);

@@ -63,9 +63,9 @@ struct ScoreArgs {
     uint32_t* yhist;         // [n][256] (pre-zeroed) or nullptr
     uint32_t* vhist;         // [n][256] (pre-zeroed) or nullptr
     uint8_t* vplane;         // [n][n_pixels] or nullptr
-    uint32_t shift24;        // 0x01000000, passed at run time (hsv_half2.cuh, PSD_V7_ADDR 1)
+    uint32_t shift24;        // 0x01000000, passed at run time: the kernel derives a zero the compiler cannot fold from it
 };
-int launch_score(const ScoreArgs& a, uint32_t features, int variant, cudaStream_t stream);
+int launch_score(const ScoreArgs& a, uint32_t features, bool generic_only, cudaStream_t stream);
 int score_kernel_smem_bytes();
 
 // ---- resize (resize_kernel.cu) ----
@@ -83,17 +83,14 @@ struct EdgeBuffers {
     uint8_t* vplane;    // [n][P] V of HSV (written by the score pass)
     uint32_t* vhist;    // [n][256]
     int32_t* thresholds;// [n][2] low, high
-    uint8_t* map;       // [n][P] 0 none / 1 weak / 2 strong -> after hysteresis >= 2 = edge
-    int32_t* labels;    // [n][P] union-find parents of the edge pixels (hysteresis)
-    int32_t* tile_rec;  // [n][tiles][16] strong tile-local roots found by psd_hyst_tile_kernel
-    uint8_t* tmp;       // [P] scratch for debug taps
-    uint32_t* bits_in;  // [n][H][Wq] edge pixels, 32 per word
+    uint32_t* cand;     // [n][H][Wq] Canny candidates (weak or strong pixels), 32 per word
+    uint32_t* bits_in;  // [n][H][Wq] edge pixels: strong pixels after classify, the Canny map after hysteresis
     uint32_t* bits_row; // [n][H][Wq] row-dilated
     uint32_t* bits_dil; // [n][H][Wq] dilated edges
     uint32_t* carry_bits; // [H][Wq] dilated edges of the predecessor frame
-    int32_t* changed;   // device flags, one per launch of a hysteresis round
-    uint8_t* dirty;     // [2][n][tiles] per-tile changed bytes (double-buffered)
-    int32_t* changed_host; // pinned
+    uint8_t* tmp;       // [P] scratch for debug taps
+    uint8_t* dirty;     // [2][n][tiles] hysteresis: tiles to revisit (double-buffered by round parity)
+    int32_t* hyst_flags;// [3] hysteresis: "some tile changed" per round (rotating)
 };
 int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
                  psd_frame_sums* sums, cudaStream_t stream);

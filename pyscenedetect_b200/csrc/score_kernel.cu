@@ -20,31 +20,24 @@ namespace psd {
 
 constexpr int kPxPerThread = 16;
 
-// per-variant launch shape: variant 4 carries a 64 KB replicated LUT, so it runs one large CTA
-// per SM; the table-free variants run three 256-thread CTAs per SM.
-template <int VARIANT>
+// generic kernel shape: table-free arithmetic, three 256-thread CTAs per SM
 struct Shape {
-    static constexpr int kThreads = (VARIANT == 4) ? 768 : 256;
-    static constexpr int kStages = (VARIANT == 4) ? 3 : 4;
-    static constexpr int kMinBlocks = (VARIANT == 4) ? 1 : 3;
-    static constexpr int kLutFloats = (VARIANT == 4) ? 256 * 64 : 4;
+    static constexpr int kThreads = 256;
+    static constexpr int kStages = 4;
+    static constexpr int kMinBlocks = 3;
     static constexpr int kStripPx = kThreads * kPxPerThread;
     static constexpr int kStripBytes = kStripPx * 3;
 };
 
-template <int VARIANT>
 struct __align__(128) ScoreSmem {
-    uint8_t ring[Shape<VARIANT>::kStages][Shape<VARIANT>::kStripBytes];
-    float lut[Shape<VARIANT>::kLutFloats];
-    unsigned long long full[Shape<VARIANT>::kStages];
-    int32_t sdiv[256];
-    int32_t hdiv[256];
+    uint8_t ring[Shape::kStages][Shape::kStripBytes];
+    unsigned long long full[Shape::kStages];
     uint32_t acc[2][8];        // per-frame CTA partials: sadH, sadS, sadV, bgr (double-buffered)
     uint32_t yhist[2][256];
     uint32_t vhist[2][256];
 };
 
-int score_kernel_smem_bytes() { return (int)sizeof(ScoreSmem<2>); }
+int score_kernel_smem_bytes() { return (int)sizeof(ScoreSmem); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -100,13 +93,12 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int 
     }
 }
 
-template <uint32_t F, int VARIANT>
-__global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMinBlocks)
-    psd_score_kernel(const ScoreArgs a) {
-    constexpr int kThreads = Shape<VARIANT>::kThreads, kStages = Shape<VARIANT>::kStages;
-    constexpr int kStripPx = Shape<VARIANT>::kStripPx, kStripBytes = Shape<VARIANT>::kStripBytes;
+template <uint32_t F>
+__global__ void __launch_bounds__(Shape::kThreads, Shape::kMinBlocks) psd_score_kernel(const ScoreArgs a) {
+    constexpr int kThreads = Shape::kThreads, kStages = Shape::kStages;
+    constexpr int kStripPx = Shape::kStripPx, kStripBytes = Shape::kStripBytes;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    ScoreSmem<VARIANT>& sm = *reinterpret_cast<ScoreSmem<VARIANT>*>(smem_raw);
+    ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(smem_raw);
     constexpr bool kHSV = (F & PSD_F_HSV) != 0;
     constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
     constexpr bool kYH = (F & PSD_F_YHIST) != 0;
@@ -133,17 +125,8 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
     };
 
     for (int i = tid; i < 256; i += kThreads) {
-        // sdiv[i] = rint((255<<12)/i), hdiv[i] = rint((180<<12)/(6i)); __double2int_rn = round-half-even
-        sm.sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
-        sm.hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
         sm.yhist[0][i] = sm.yhist[1][i] = 0;
         sm.vhist[0][i] = sm.vhist[1][i] = 0;
-    }
-    LutView lut{0u, 0u};
-    if (VARIANT == 4 && kHSV) {
-        lut_fill(sm.lut, tid, kThreads);
-        lut.s_addr = smem_u32(sm.lut) + (tid & 31) * 4;
-        lut.h_addr = lut.s_addr + 128;
     }
     if (tid < 16) sm.acc[tid >> 3][tid & 7] = 0;
     if (tid == 0) {
@@ -216,10 +199,7 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
         uint32_t sad_h = 0, sad_s = 0, sad_v = 0, bsum = 0;
         if (kHSV) {
             Px16 cur;
-            if (VARIANT == 4)
-                hsv16_v4(w, cur, lut);
-            else
-                hsv16<VARIANT>(w, cur, sm.sdiv, sm.hdiv);
+            hsv16_f32x2(w, cur);
             if (prev_valid) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -325,7 +305,7 @@ __global__ void __launch_bounds__(Shape<VARIANT>::kThreads, Shape<VARIANT>::kMin
 #define PSD_WS_STAGES 4
 #endif
 #ifndef PSD_WS_UNROLL
-#define PSD_WS_UNROLL 2  // frames per consumer loop body: 2 (stage pair toggles) or 4 (all stage offsets immediate)
+#define PSD_WS_UNROLL 4  // frames per consumer loop body: 2 (stage pair toggles) or 4 (all stage offsets immediate)
 #endif
 #ifndef PSD_WS_SYNCWARP
 // 0: no __syncwarp() in front of lane 0's EMPTY arrival.  The warp is converged there (every branch of the
@@ -364,10 +344,17 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
     asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+#ifndef PSD_WS_WAITMODE
+#define PSD_WS_WAITMODE 0  // 0: try_wait with a suspend-time hint, 1: plain try_wait, 2: test_wait first, then try_wait
+#endif
+#ifndef PSD_WS_PAIRWAIT
+#define PSD_WS_PAIRWAIT 0  // 1: the consumer checks the FULL barriers of two consecutive frames back to back
+#endif
 // try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase
 // completes instead of burning issue slots of its sub-partition in a poll loop
 template <int OFF>
 __device__ __forceinline__ void mbar_wait_hint_off(uint32_t bar, uint32_t parity) {
+#if PSD_WS_WAITMODE == 0
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -379,6 +366,33 @@ __device__ __forceinline__ void mbar_wait_hint_off(uint32_t bar, uint32_t parity
         "}" ::"r"(bar),
         "r"(parity), "r"(20000u), "n"(OFF)
         : "memory");
+#elif PSD_WS_WAITMODE == 1
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%2], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "n"(OFF)
+        : "memory");
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0+%3], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%3], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(20000u), "n"(OFF)
+        : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, uint32_t parity) {
     mbar_wait_hint_off<0>(smem_u32(bar), parity);
@@ -434,23 +448,31 @@ struct WsAddr {  // shared-window addresses of the current loop body's first sta
 
 // One frame of the consumer loop at stage (body base + J).  `sad_acc`: accumulator base the SADs go to (the
 // stage's real per-lane words, or the sink); `mine`: the frame is not the halo and the thread owns pixels.
-template <uint32_t F, int HV, int J>
+template <uint32_t F, int J>
 __device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const WsAddr& ad, uint32_t parity, int stage0,
                                         uint32_t sad_acc, bool mine, int fi, int my_px, int lane, uint32_t zero,
-                                        const LutView& lut, const LutView7& lut7, const Px16& prev, Px16& cur) {
+                                        const LutView7& lut7, const Px16& prev, Px16& cur) {
     constexpr bool kHSV = (F & PSD_F_HSV) != 0;
     constexpr bool kSUM = (F & PSD_F_BGRSUM) != 0;
     constexpr bool kYH = (F & PSD_F_YHIST) != 0;
     constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
+#if PSD_WS_PAIRWAIT
+    // even frame of a body: check this frame's and the next frame's barrier back to back, so the latency of the
+    // second check hides behind the first; the odd frame then finds its data without asking again
+    if ((J & 1) == 0) {
+        mbar_wait_hint_off<J * 8>(ad.full, parity);
+        mbar_wait_hint_off<J * 8 + 8>(ad.full, parity);
+    }
+#else
     mbar_wait_hint_off<J * 8>(ad.full, parity);
+#endif
     uint32_t w[12];
     // idle threads of a partial last strip read stale ring bytes; they never contribute (sink / mine)
     lds128_off<J * kWsStripBytes>(ad.ring, w[0], w[1], w[2], w[3]);
     lds128_off<J * kWsStripBytes + 16>(ad.ring, w[4], w[5], w[6], w[7]);
     lds128_off<J * kWsStripBytes + 32>(ad.ring, w[8], w[9], w[10], w[11]);
     if (kHSV) {
-        if (HV >= 7) hsv16_v7<HV == 8>(w, cur, lut7, a.shift24);
-        else hsv16_v4(w, cur, lut);
+        hsv16_v7(w, cur, lut7);
         // one dependent VABSDIFF4.ACC chain per plane (the compiler otherwise splits each into four
         // zero-seeded accumulators plus an IADD3 tree: 12 extra issue slots per frame)
         uint32_t sad_h = sad4_acc(cur.h[0], prev.h[0], zero), sad_s = sad4_acc(cur.s[0], prev.s[0], zero),
@@ -506,9 +528,7 @@ __device__ __forceinline__ void ws_null_step(const WsAddr& ad, uint32_t parity, 
     if (lane == 0) mbar_arrive_off<kWsStages * 8 + J * 8>(ad.full);
 }
 
-// HV selects the HSV arithmetic: 4 = scalar float LUT formulation (hsv_math.cuh), 7 = pixel pairs in
-// half2 / u16x2 lanes (hsv_half2.cuh).  Both are bit-exact; 7 needs ~20 % fewer issue slots.
-template <uint32_t F, int HV>
+template <uint32_t F>
 __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
@@ -531,10 +551,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
         (&sm.accl_seen[0][0][0])[i] = 0;
         (&sm.accl_sink[0][0][0])[i] = 0;
     }
-    if (kHSV) {
-        if (HV >= 7) lut_fill7(sm.lut, tid, kWsThreads);
-        else lut_fill(sm.lut, tid, kWsThreads);
-    }
+    if (kHSV) lut_fill7(sm.lut, tid, kWsThreads);
     if (tid == 0) {
         for (int s = 0; s < kWsStages; ++s) {
             mbar_init(&sm.full[s], 1);
@@ -632,9 +649,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
     }
 
     // ===================== consumer warps =====================
-    LutView lut{0u, 0u};
-    lut.s_addr = smem_u32(sm.lut) + lane * 4;
-    lut.h_addr = lut.s_addr + 128;
     const LutView7 lut7 = make_lut7(smem_u32(sm.lut), lane);
     // a zero the compiler cannot see through: it stays in one register for the whole loop instead of
     // being re-materialised (CS2R) in front of every accumulation chain
@@ -673,23 +687,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) psd_score_ws_kernel(const Score
 #pragma unroll 1
         for (; k + U <= n; k += U) {
             const bool first_mine = active && (wi.it_begin + k >= 1);
-            ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, first_mine, fbase + k, my_px, lane, zero, lut, lut7, P0, P1);
-            ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+            ws_step<F, 0>(a, sm, ad, parity, stage0, acc_first, first_mine, fbase + k, my_px, lane, zero, lut7, P0, P1);
+            ws_step<F, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut7, P1, P0);
             if (U == 4) {
-                ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
-                ws_step<F, HV, 3 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 3, my_px, lane, zero, lut, lut7, P1, P0);
+                ws_step<F, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut7, P0, P1);
+                ws_step<F, 3 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 3, my_px, lane, zero, lut7, P1, P0);
             }
             next_body(acc0);
             acc_first = ad.acc;
         }
         if (k < n) {  // last, partial body of the item: real frames first, then the padding slots
             const int r = n - k;  // 1 .. U-1
-            ws_step<F, HV, 0>(a, sm, ad, parity, stage0, acc_first, active && (wi.it_begin + k >= 1), fbase + k, my_px,
-                              lane, zero, lut, lut7, P0, P1);
+            ws_step<F, 0>(a, sm, ad, parity, stage0, acc_first, active && (wi.it_begin + k >= 1), fbase + k, my_px,
+                              lane, zero, lut7, P0, P1);
             if (U == 4) {
-                if (r > 1) ws_step<F, HV, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut, lut7, P1, P0);
+                if (r > 1) ws_step<F, 1>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 1, my_px, lane, zero, lut7, P1, P0);
                 else ws_null_step<1>(ad, parity, lane);
-                if (r > 2) ws_step<F, HV, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut, lut7, P0, P1);
+                if (r > 2) ws_step<F, 2 % U>(a, sm, ad, parity, stage0, ad.acc, active, fbase + k + 2, my_px, lane, zero, lut7, P0, P1);
                 else ws_null_step<2 % U>(ad, parity, lane);
                 ws_null_step<3 % U>(ad, parity, lane);
             } else {
@@ -716,7 +730,7 @@ static int pick_chunks(int n_frames, int n_strips, int grid) {
     return best;
 }
 
-template <uint32_t F, int HV>
+template <uint32_t F>
 static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
     const int smem = (int)sizeof(WsSmem);
     static int sm_count = 0;
@@ -725,7 +739,7 @@ static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
         PSD_CUDA(cudaGetDevice(&dev));
         PSD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PSD_CUDA(cudaFuncSetAttribute(psd_score_ws_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     a.shift24 = 0x01000000u;
     a.features = F;
     a.n_strips = n_ws_strips;
@@ -734,17 +748,15 @@ static int launch_ws(ScoreArgs a, int n_ws_strips, cudaStream_t stream) {
     const int64_t items = (int64_t)a.n_chunks * n_ws_strips;
     PSD_REQUIRE(items > 0 && items < 2147483647LL, "score work items out of range (%lld)", (long long)items);
     const int grid = (int)(items < sm_count ? items : sm_count);
-    psd_score_ws_kernel<F, HV><<<grid, kWsThreads, smem, stream>>>(a);
+    psd_score_ws_kernel<F><<<grid, kWsThreads, smem, stream>>>(a);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;
 }
 
-static int dispatch_ws(const ScoreArgs& a, uint32_t f, int hv, int n_ws_strips, cudaStream_t s) {
+static int dispatch_ws(const ScoreArgs& a, uint32_t f, int n_ws_strips, cudaStream_t s) {
     switch (f & 15u) {
-        // masks without the HSV bit do not depend on HV: one instantiation
-#define CASE(F) case F: if (!((F) & PSD_F_HSV) || hv == 4) return launch_ws<F, 4>(a, n_ws_strips, s); \
-                        return hv == 8 ? launch_ws<F, 8>(a, n_ws_strips, s) : launch_ws<F, 7>(a, n_ws_strips, s);
+#define CASE(F) case F: return launch_ws<F>(a, n_ws_strips, s);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
         CASE(9) CASE(11) CASE(13) CASE(15)
 #undef CASE
@@ -754,24 +766,22 @@ static int dispatch_ws(const ScoreArgs& a, uint32_t f, int hv, int n_ws_strips, 
     }
 }
 
-template <uint32_t F, int VARIANT>
+template <uint32_t F>
 static int launch_one(ScoreArgs a, cudaStream_t stream) {
-    const int smem = (int)sizeof(ScoreSmem<VARIANT>);
-    PSD_CUDA(cudaFuncSetAttribute(psd_score_kernel<F, VARIANT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    a.n_strips = (a.n_pixels - a.px_base + Shape<VARIANT>::kStripPx - 1) / Shape<VARIANT>::kStripPx;
+    const int smem = (int)sizeof(ScoreSmem);
+    PSD_CUDA(cudaFuncSetAttribute(psd_score_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    a.n_strips = (a.n_pixels - a.px_base + Shape::kStripPx - 1) / Shape::kStripPx;
     const int64_t grid = (int64_t)a.n_chunks * a.n_strips;
     PSD_REQUIRE(grid > 0 && grid < 2147483647LL, "score grid out of range (%lld)", (long long)grid);
-    psd_score_kernel<F, VARIANT><<<(unsigned)grid, Shape<VARIANT>::kThreads, smem, stream>>>(a);
+    psd_score_kernel<F><<<(unsigned)grid, Shape::kThreads, smem, stream>>>(a);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;
 }
 
-template <int VARIANT>
 static int dispatch(const ScoreArgs& a, uint32_t f, cudaStream_t s) {
     switch (f & 15u) {
-#define CASE(F) case F: return launch_one<F, VARIANT>(a, s);
+#define CASE(F) case F: return launch_one<F>(a, s);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
         CASE(9) CASE(11) CASE(13) CASE(15)
 #undef CASE
@@ -781,7 +791,7 @@ static int dispatch(const ScoreArgs& a, uint32_t f, cudaStream_t s) {
     }
 }
 
-int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStream_t stream) {
+int launch_score(const ScoreArgs& a_in, uint32_t features, bool generic_only, cudaStream_t stream) {
     ScoreArgs a = a_in;
     if (features & PSD_F_EDGES) features |= PSD_F_HSV;
     PSD_REQUIRE(a.n_frames > 0 && a.n_pixels > 0, "empty score launch");
@@ -795,59 +805,36 @@ int launch_score(const ScoreArgs& a_in, uint32_t features, int variant, cudaStre
         a.chunk_frames = frames_per_chunk;
         a.n_chunks = (a.n_frames + a.chunk_frames - 1) / a.chunk_frames;
     };
-    if (variant == 5 || variant == 7 || variant == 8) {
-        // persistent warp-specialised kernel on the 12288-pixel strips, generic kernel (variant 2) on
-        // the remainder; an unaligned input goes entirely through the generic kernel
-        int n_ws = a.tma_ok ? a.n_pixels / kWsStripPx : 0;
-        int covered = n_ws * kWsStripPx;
-        const int tail = a.n_pixels - covered;
-        if (n_ws > 0 && tail > 0 && (tail % 16) == 0) {  // partial last strip stays in the same kernel
-            n_ws += 1;
-            covered = a.n_pixels;
-        }
-        if (n_ws > 0) {
-            a.n_chunks = 0;  // launch_ws balances the time chunks over the SMs
-            if (const char* c = getenv("PSD_CHUNKS")) a.n_chunks = atoi(c) > 0 ? atoi(c) : 0;
-            int rc = dispatch_ws(a, features, variant == 5 ? 4 : variant, n_ws, stream);
-            if (rc) return rc;
-            a.px_base = covered;
-            a.write_has_prev = 0;
-            if (a.px_base >= a.n_pixels) return PSD_OK;
-            generic_chunks(16);  // the remainder is a sliver of the frame: short time chunks give it enough CTAs
-        } else {
-            generic_chunks(64);
-        }
-        return dispatch<2>(a, features, stream);
+    // persistent warp-specialised kernel on the 12288-pixel strips, generic kernel on the remainder; an
+    // unaligned input (or PSD_CFG_GENERIC_KERNEL, the cross-check switch) goes entirely through the generic kernel
+    int n_ws = (a.tma_ok && !generic_only) ? a.n_pixels / kWsStripPx : 0;
+    int covered = n_ws * kWsStripPx;
+    const int tail = a.n_pixels - covered;
+    if (n_ws > 0 && tail > 0 && (tail % 16) == 0) {  // partial last strip stays in the same kernel
+        n_ws += 1;
+        covered = a.n_pixels;
     }
-    generic_chunks(64);
-    // variant 1: scalar integer + MUFU (first correct version), 2: packed f32x2, 4: float LUT
-    switch (variant) {
-        case 1: return dispatch<1>(a, features, stream);
-        case 2: return dispatch<2>(a, features, stream);
-        case 4: return dispatch<4>(a, features, stream);
-        default:
-            set_error("hsv variant %d is not built into the score kernel (1, 2, 4, 5, 7, 8 are)", variant);
-            return PSD_ERR_INVALID;
+    if (n_ws > 0) {
+        a.n_chunks = 0;  // launch_ws balances the time chunks over the SMs
+        int rc = dispatch_ws(a, features, n_ws, stream);
+        if (rc) return rc;
+        a.px_base = covered;
+        a.write_has_prev = 0;
+        if (a.px_base >= a.n_pixels) return PSD_OK;
+        generic_chunks(16);  // the remainder is a sliver of the frame: short time chunks give it enough CTAs
+    } else {
+        generic_chunks(64);
     }
+    return dispatch(a, features, stream);
 }
 
 // ---- test hook: the same device functions on a flat pixel array ----
-template <int VARIANT>
+// FAST = the warp-specialised kernel's arithmetic (hsv_half2.cuh), else the generic kernel's (hsv_math.cuh)
+template <bool FAST>
 __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_t* h, uint8_t* s,
-                                    uint8_t* v, uint8_t* y, uint32_t shift24) {
+                                    uint8_t* v, uint8_t* y) {
     extern __shared__ __align__(128) float lutmem[];
-    __shared__ int32_t sdiv[256], hdiv[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        sdiv[i] = i ? __double2int_rn(1044480.0 / (double)i) : 0;
-        hdiv[i] = i ? __double2int_rn(737280.0 / (6.0 * (double)i)) : 0;
-    }
-    LutView lut{0u, 0u};
-    if (VARIANT == 7 || VARIANT == 8) lut_fill7(lutmem, threadIdx.x, blockDim.x);
-    if (VARIANT == 4 || VARIANT == 6) {
-        lut_fill(lutmem, threadIdx.x, blockDim.x);
-        lut.s_addr = smem_u32(lutmem) + (threadIdx.x & 31) * 4;
-        lut.h_addr = lut.s_addr + 128;
-    }
+    if (FAST) lut_fill7(lutmem, threadIdx.x, blockDim.x);
     const LutView7 lut7 = make_lut7(smem_u32(lutmem), threadIdx.x & 31);
     __syncthreads();
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
@@ -859,14 +846,8 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
         w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
         w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
         Px16 o;
-        if (VARIANT == 7 || VARIANT == 8)
-            hsv16_v7<VARIANT == 8>(w, o, lut7, shift24);
-        else if (VARIANT == 6)
-            hsv16_v4pair(w, o, lut);
-        else if (VARIANT == 4)
-            hsv16_v4(w, o, lut);
-        else
-            hsv16<VARIANT>(w, o, sdiv, hdiv);
+        if (FAST) hsv16_v7(w, o, lut7);
+        else hsv16_f32x2(w, o);
         *reinterpret_cast<uint4*>(h + g * 16) = make_uint4(o.h[0], o.h[1], o.h[2], o.h[3]);
         *reinterpret_cast<uint4*>(s + g * 16) = make_uint4(o.s[0], o.s[1], o.s[2], o.s[3]);
         *reinterpret_cast<uint4*>(v + g * 16) = make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]);
@@ -875,13 +856,12 @@ __global__ void psd_test_hsv_kernel(const uint8_t* bgr, int64_t n_groups, uint8_
     }
 }
 
-template <int VARIANT>
+template <bool FAST>
 static int run_test_hsv(const uint8_t* d_bgr, int64_t groups, uint8_t* dh, uint8_t* ds, uint8_t* dv,
                         uint8_t* dy) {
-    const int smem = (VARIANT == 4 || VARIANT >= 6) ? 65536 : 0;
-    PSD_CUDA(cudaFuncSetAttribute(psd_test_hsv_kernel<VARIANT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    psd_test_hsv_kernel<VARIANT><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy, 0x01000000u);
+    const int smem = FAST ? 65536 : 0;
+    PSD_CUDA(cudaFuncSetAttribute(psd_test_hsv_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    psd_test_hsv_kernel<FAST><<<148 * 2, 256, smem>>>(d_bgr, groups, dh, ds, dv, dy);
     PSD_CHECK_LAUNCH();
     return PSD_OK;
 }
@@ -892,7 +872,8 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
                             uint8_t* s_out, uint8_t* v_out, uint8_t* y_out, int variant) {
     using namespace psd;
     PSD_REQUIRE(n_pixels > 0 && (n_pixels % 16) == 0, "n_pixels must be a positive multiple of 16");
-    PSD_REQUIRE((variant >= 0 && variant <= 4) || (variant >= 6 && variant <= 8), "unknown hsv variant %d", variant);
+    PSD_REQUIRE(variant == 2 || variant == 7,
+                "unknown hsv arithmetic %d (2 = generic kernel, 7 = warp-specialised kernel)", variant);
     PSD_CUDA(cudaSetDevice(device));
     uint8_t *d_bgr = nullptr, *d_out = nullptr;
     PSD_CUDA(cudaMalloc(&d_bgr, (size_t)n_pixels * 3));
@@ -902,17 +883,8 @@ extern "C" int psd_test_hsv(int device, const uint8_t* bgr_host, int64_t n_pixel
     uint8_t* ds = d_out + n_pixels;
     uint8_t* dv = d_out + 2 * n_pixels;
     uint8_t* dy = d_out + 3 * n_pixels;
-    int rc;
-    switch (variant) {
-        case 0: rc = run_test_hsv<0>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 1: rc = run_test_hsv<1>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 2: rc = run_test_hsv<2>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 3: rc = run_test_hsv<3>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 4: rc = run_test_hsv<4>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 7: rc = run_test_hsv<7>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        case 8: rc = run_test_hsv<8>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-        default: rc = run_test_hsv<6>(d_bgr, n_pixels / 16, dh, ds, dv, dy); break;
-    }
+    int rc = variant == 7 ? run_test_hsv<true>(d_bgr, n_pixels / 16, dh, ds, dv, dy)
+                          : run_test_hsv<false>(d_bgr, n_pixels / 16, dh, ds, dv, dy);
     if (rc) return rc;
     count_launch();
     PSD_CUDA(cudaDeviceSynchronize());

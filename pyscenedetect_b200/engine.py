@@ -75,7 +75,7 @@ class Engine:
 
     def __init__(self, src_width: int, src_height: int, features: int, width: int | None = None,
                  height: int | None = None, device: int = 0, max_batch: int = 64,
-                 edge_kernel_size: int = 0):
+                 edge_kernel_size: int = 0, generic_kernel: bool = False):
         self._lib = _capi.load()
         cfg = _capi.PsdConfig()
         cfg.struct_size = C.sizeof(_capi.PsdConfig)
@@ -86,6 +86,7 @@ class Engine:
         cfg.features = int(features)
         cfg.edge_kernel_size = int(edge_kernel_size)
         cfg.max_batch = int(max_batch)
+        cfg.flags = _capi.CFG_GENERIC_KERNEL if generic_kernel else 0  # cross-check switch (tests)
         h = C.c_void_p()
         check(self._lib.psd_engine_create(C.byref(cfg), C.byref(h)), "psd_engine_create")
         self._h = h

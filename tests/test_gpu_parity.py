@@ -122,7 +122,7 @@ def test_batched_scene_manager_matches_reference_golden(lib, name, batch):
         _check_stats(case, stats, frames.shape[0])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6, 7, 8])
+@pytest.mark.parametrize("variant", [2, 7])  # 2 = generic kernel arithmetic, 7 = warp-specialised kernel arithmetic
 def test_hsv_and_y_exhaustive_2_24(lib, variant):
     """Every BGR colour through the device functions of the fused kernel vs cv2."""
     v = np.arange(1 << 24, dtype=np.uint32)
@@ -280,6 +280,66 @@ def test_edge_intermediates_match_cv2(lib, shape):
     eng.close()
 
 
+def test_edge_path_matches_cv2_at_1080p(lib):
+    """BASELINE.json configs[2] size: Canny map, dilated edges and the edge SAD of 1920x1080 frames vs cv2
+    (30 x 34 hysteresis tiles, k = 13, components spanning many tiles).  The blurred-noise frames are dense
+    with short components, the ramp-plus-noise frame has long weak chains that only resolve over many
+    rounds across tile borders, the raw noise frame is the worst case for the candidate density."""
+    from pyscenedetect_b200.engine import F_EDGES, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    w, h = 1920, 1080
+    frames = render_frames(ScenePlan(4, seed=9, min_len=2, max_len=3).params, w, h)
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    ramp = ((xx * 255) // (w - 1)).astype(np.uint8)
+    weak = np.clip(ramp[..., None].astype(np.int16) + rng.integers(-9, 10, (h, w, 3)), 0, 255).astype(np.uint8)
+    extra = np.stack([cv2.GaussianBlur(noise, (5, 5), 0), cv2.GaussianBlur(noise, (15, 15), 0), weak, noise])
+    frames = np.concatenate([frames, extra])
+    eng = Engine(w, h, F_EDGES, max_batch=8)
+    eng.submit(frames)
+    k = eng.edge_kernel_size
+    assert k == R.estimated_kernel_size(w, h) == 13
+    kernel = np.ones((k, k), np.uint8)
+    sums = eng.read_sums()
+    prev = None
+    for i, f in enumerate(frames):
+        lum = cv2.split(cv2.cvtColor(f, cv2.COLOR_BGR2HSV))[2]
+        low, high = M.canny_thresholds(float(np.median(lum)))
+        assert np.array_equal(eng.debug_plane(2, i), cv2.Canny(lum, low, high)), i
+        want = R.detect_edges(lum, kernel)
+        assert np.array_equal(eng.debug_plane(3, i), want), i
+        if prev is not None:
+            assert int(sums["sad_edges"][i]) == M.sad(want, prev), i
+        prev = want
+    eng.close()
+
+
+def test_histogram_path_matches_oracle_at_4k(lib):
+    """BASELINE.json configs[3] size: the 256-bin Y histogram of 3840x2160 frames vs numpy.bincount of the
+    oracle's Y plane (= cv2 COLOR_BGR2YUV), and hist_diff vs cv2.compareHist(CORREL) on cv2's own histograms."""
+    from pyscenedetect_b200.engine import F_YHIST, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    w, h = 3840, 2160
+    frames = render_frames(ScenePlan(3, seed=5, min_len=1, max_len=2).params, w, h)
+    rng = np.random.default_rng(8)
+    frames = np.concatenate([frames, rng.integers(0, 256, (1, h, w, 3), dtype=np.uint8)])
+    eng = Engine(w, h, F_YHIST, max_batch=4)
+    eng.submit(frames)
+    yh = eng.read_yhist()
+    diffs = eng.scan_hist_correl(256)
+    eng.close()
+    prev = None
+    for i, f in enumerate(frames):
+        y = cv2.split(cv2.cvtColor(f, cv2.COLOR_BGR2YUV))[0]
+        assert np.array_equal(M.bgr_to_y(f), y)
+        assert np.array_equal(yh[i], np.bincount(y.ravel(), minlength=256)), i
+        hist = R.calculate_histogram(f, bins=256)
+        if prev is not None:
+            assert abs(diffs[i] - cv2.compareHist(prev, hist, cv2.HISTCMP_CORREL)) < 1e-9, i
+        prev = hist
+
+
 def test_errors_are_loud(lib):
     from pyscenedetect_b200 import FrameTimecode
     from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector
@@ -303,10 +363,11 @@ def test_errors_are_loud(lib):
 
 
 @pytest.mark.parametrize("shape", [(1920, 1080), (640, 360), (3840, 2160), (1000, 37)])
-def test_kernel_variants_agree_at_full_size(lib, shape, monkeypatch):
-    """Every build of the fused pass (scalar, f32x2, LUT, warp-specialised + remainder) produces the
-    same integer sums/histograms on full-size frames; the first frames are also checked against
-    the integer oracle.  (1920x1080 and 3840x2160 exercise the warp-specialised strips.)"""
+def test_kernel_variants_agree_at_full_size(lib, shape):
+    """The persistent warp-specialised kernel (+ generic remainder) and the generic kernel alone produce
+    the same integer sums/histograms on full-size frames; the first frames are also checked against
+    the integer oracle.  (1920x1080 and 3840x2160 exercise the warp-specialised strips, 1000x37 the
+    partial strip + remainder split.)"""
     from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, DeviceBuffer, Engine, synth_frames_device
     from pyscenedetect_b200.synth import ScenePlan
     w, h = shape
@@ -315,9 +376,8 @@ def test_kernel_variants_agree_at_full_size(lib, shape, monkeypatch):
     buf = DeviceBuffer(n * w * h * 3)
     synth_frames_device(buf.ptr, plan.params, w, h)
     ref = None
-    for variant in ("5", "7", "8", "4", "2", "1"):
-        monkeypatch.setenv("PSD_HSV_VARIANT", variant)
-        eng = Engine(w, h, F_HSV | F_BGRSUM | F_YHIST, max_batch=128)
+    for variant in ("fused", "generic"):
+        eng = Engine(w, h, F_HSV | F_BGRSUM | F_YHIST, max_batch=128, generic_kernel=(variant == "generic"))
         eng.submit_device(buf.ptr, n)
         got = (eng.read_sums().tobytes(), eng.read_yhist().tobytes())
         if ref is None:

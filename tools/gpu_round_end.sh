@@ -12,7 +12,7 @@ timeout 300 python bench.py --auto-downscale --frames 4096 --steps 5 --warmup 3 
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --frames 2048 --steps 2 --warmup 1 --no-cpu --no-e2e > $O/ncu_launches.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:psd_score_ws_kernel -s 2 -c 1 -f -o $O/ws_v7_final python bench.py --frames 1024 --steps 2 --warmup 1 --no-cpu --no-e2e > $O/ncu_ws.log 2>&1
 timeout 400 ncu --set full --clock-control none -k regex:psd_score_ws_kernel -s 2 -c 1 -f -o $O/ws_hist_final python bench.py --detector histogram --frames 1024 --steps 2 --warmup 1 --no-cpu --no-e2e > $O/ncu_hist.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:psd_hyst_tile_kernel -s 1 -c 1 -f -o $O/hyst_tile python bench.py --detector content_edges --frames 512 --steps 1 --warmup 1 --no-cpu --no-e2e > $O/ncu_tile.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:psd_canny_classify_bits_kernel -s 1 -c 1 -f -o $O/classify_bits python bench.py --detector content_edges --frames 512 --steps 1 --warmup 1 --no-cpu --no-e2e > $O/ncu_tile.log 2>&1
 for f in $O/bench*.json; do python - "$f" <<'PY'
 import json,sys
 try:

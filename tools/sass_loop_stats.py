@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Instruction histogram of the consumer loop of psd_score_ws_kernel<F=HSV, HV=7> in a built library
+"""Instruction histogram of the consumer loop of psd_score_ws_kernel<F=HSV> in a built library
 (no GPU needed):  python tools/sass_loop_stats.py [path/to/lib.so] [--list]
 Classes follow the pipe model measured in profiles/r01*_pipes*.txt (alu half / fma half / wide / other)."""
 import collections
@@ -7,7 +7,7 @@ import re
 import subprocess
 import sys
 
-FUNC = "_ZN3psd19psd_score_ws_kernelILj1ELi7EEEvNS_9ScoreArgsE"
+FUNC = "_ZN3psd19psd_score_ws_kernelILj1EEEvNS_9ScoreArgsE"
 LINE = re.compile(r"^\s+/\*([0-9a-f]{4,5})\*/\s+(?:@!?U?P\d\s+)?([A-Za-z0-9_.]+)")
 ALU = ("PRMT", "LOP3", "SHF", "VIMNMX", "VHMNMX", "HSET2", "FMNMX3", "VABSDIFF", "SEL", "ISETP", "PLOP3", "LEA",
        "VIADD", "MOV", "FSEL", "FSETP", "I2IP", "F2FP", "SGXT", "BMSK")
@@ -36,8 +36,12 @@ def loop_rows(lib):
         m = re.search(r"BRA\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", l)
         if op.startswith("BRA") and m and int(m.group(1), 16) < a and int(m.group(1), 16) in idx:
             bodies.append(rows[idx[int(m.group(1), 16)]:i + 1])
-    cands = [b for b in bodies if sum(op == "LDS.128" for _, op, _ in b) >= 6]
-    return min(cands, key=len), len(rows)
+    # the consumer loop is the innermost loop around the most LDS.128 (3 per frame, 2 or 4 frames per body)
+    def n_lds(b):
+        return sum(op == "LDS.128" for _, op, _ in b)
+    cands = [b for b in bodies if n_lds(b) >= 6 and n_lds(b) % 3 == 0]
+    best = max(n_lds(b) for b in cands if n_lds(b) <= 12)
+    return min((b for b in cands if n_lds(b) == best), key=len), len(rows)
 
 
 def main():
