@@ -56,6 +56,11 @@ def parse_args():
     ap.add_argument("--parity-frames", type=int, default=None,
                     help="frames of the timed run re-scored with the oracle (default: the cpu sample, 48 with --no-cpu)")
     ap.add_argument("--ref-frames-per-proc", type=int, default=64, help="reference arm: frames per process per step")
+    ap.add_argument("--resident-gb", type=float, default=150.0,
+                    help="HBM budget for resident input per GPU; a larger shard cycles a resident ring of distinct frames")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json configs[4]: one line per (size, total frames) cell, strong scaling over the ranks")
+    ap.add_argument("--sweep-cells", default="640x360,1280x720,1920x1080,3840x2160:1000,10000,100000")
     ap.add_argument("--auto-downscale", action="store_true",
                     help="score at SceneManager's default auto-downscaled size (256 px wide) instead of full resolution")
     return ap.parse_args()
@@ -314,7 +319,7 @@ def run_ours(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = local
     torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     lib = _capi.load()
@@ -334,9 +339,16 @@ def run_ours(args):
         first = rank * N
     plan = ScenePlan(total_frames, seed=args.seed)
 
-    # ---- resident input: this rank's contiguous time range, generated on the device ----
-    frames_t = torch.empty(N * fbytes, dtype=torch.uint8, device=f"cuda:{dev}")
-    synth_frames_device(frames_t.data_ptr(), plan.params[first:first + N], W, H, device=dev)
+    # ---- resident input: this rank's contiguous time range, generated on the device.  A shard larger than the
+    #      HBM budget keeps a ring of its first R frames resident and walks it N / R times (the sequence is then
+    #      periodic; bytes read from HBM per step are unchanged) ----
+    R = N
+    free_b, _tot_b = torch.cuda.mem_get_info(dev)
+    budget = min(args.resident_gb * 1e9, 0.85 * free_b)
+    if N * fbytes > budget:
+        R = max(2, int(budget // fbytes))
+    frames_t = torch.empty(R * fbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+    synth_frames_device(frames_t.data_ptr(), plan.params[first:first + R], W, H, device=dev)
     halo_t = torch.empty(fbytes, dtype=torch.uint8, device=f"cuda:{dev}") if world > 1 else None
     torch.cuda.synchronize()
 
@@ -375,7 +387,8 @@ def run_ours(args):
             # ring shift of one frame over NCCL/NVLink: last frame -> rank+1, halo <- rank-1
             ops = []
             if rank + 1 < world:
-                ops.append(dist.P2POp(dist.isend, frames_t[(N - 1) * fbytes:], rank + 1))
+                last = (N - 1) % R
+                ops.append(dist.P2POp(dist.isend, frames_t[last * fbytes:(last + 1) * fbytes], rank + 1))
             if rank > 0:
                 ops.append(dist.P2POp(dist.irecv, halo_t, rank - 1))
             if ops:
@@ -385,7 +398,11 @@ def run_ours(args):
                 halo_ready.record(torch.cuda.current_stream())
                 ext_stream.wait_event(halo_ready)  # the engine's compute stream picks the halo up when it has landed
                 eng.set_halo_device(halo_t.data_ptr())
-        eng.submit_device(frames_t.data_ptr(), N, fbytes)
+        done = 0
+        while done < N:  # one submit unless the shard cycles a resident ring
+            k = min(R - done % R, N - done)
+            eng.submit_device(frames_t.data_ptr() + (done % R) * fbytes, k, fbytes)
+            done += k
         sp, hp = eng.device_results()
         st = eng.compute_stream  # scans are ordered after the score kernel on the engine's stream
         if args.detector in ("content", "content_edges", "adaptive"):
@@ -449,7 +466,7 @@ def run_ours(args):
     parity = None
     if args.parity_frames != 0:
         want_n = args.parity_frames if args.parity_frames else (48 if args.no_cpu else args.cpu_sample)
-        n_par = max(2, min(want_n, N)) if rank == 0 else 1
+        n_par = max(2, min(want_n, N, R)) if rank == 0 else 1
         n_dl = n_par
         sample = np.empty((n_dl, H, W, 3), dtype=np.uint8)
         _capi.check(lib.psd_memcpy_d2h(dev, sample.ctypes.data, frames_t.data_ptr(), n_dl * fbytes))
@@ -526,7 +543,8 @@ def run_ours(args):
                                           W, H, args.seed, (sw, sh)),
                 "frames_per_gpu": N, "total_frames": total_frames,
                 "parallelism": f"{world} contiguous time shards, 1-frame halo over NCCL p2p" if world > 1 else "single GPU",
-                "l2": f"inputs are {N * fbytes / 1e9:.1f} GB per step per GPU, larger than L2 (126 MB): no flush needed",
+                "l2": f"inputs are {N * fbytes / 1e9:.1f} GB per step per GPU, larger than L2 (126 MB): no flush needed"
+                      + ("" if R == N else f"; {R} distinct frames ({R * fbytes / 1e9:.1f} GB) stay resident and are walked {N / R:.2f} times per step"),
                 "timed_region": "halo exchange + fused score kernel + trailing device scan, inputs resident in HBM",
             },
             "wall_ms_per_step": wall_ms,
@@ -564,7 +582,7 @@ def run_ours(args):
         from pyscenedetect_b200.engine import bind_host_to_gpu_numa_node
         orig_affinity = os.sched_getaffinity(0)
         numa = bind_host_to_gpu_numa_node(dev)  # page-locked frames on the GPU's own NUMA node
-        ring = min(args.host_ring, N)
+        ring = min(args.host_ring, N, R)
         pin = PinnedBuffer(ring * fbytes)
         _capi.check(lib.psd_memcpy_d2h(dev, pin.array.ctypes.data, frames_t.data_ptr(), ring * fbytes))
         host_frames = pin.array.reshape(ring, H, W, 3)
@@ -622,7 +640,7 @@ def run_ours(args):
     # ---- cpu_baseline: oracle port (the reference's cv2/numpy calls) on the host cores, N=1 only ----
     if rank == 0 and world == 1 and not args.no_cpu:
         import cv2
-        ns = min(args.cpu_sample, N)
+        ns = min(args.cpu_sample, N, R)
         sample = np.empty((ns, H, W, 3), dtype=np.uint8)
         _capi.check(lib.psd_memcpy_d2h(dev, sample.ctypes.data, frames_t.data_ptr(), ns * fbytes))
         det = ref_detector(args.detector)
@@ -643,16 +661,35 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del frames_t, d_val, d_comp, d_flag
+    torch.cuda.empty_cache()
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.sweep:
+        import copy
+        sizes, totals = args.sweep_cells.split(":")
+        for size in sizes.split(","):
+            for total in totals.split(","):
+                a = copy.copy(args)
+                a.width, a.height = (int(v) for v in size.split("x"))
+                a.frames, a.scaling = int(total), "strong"
+                a.no_e2e = a.no_cpu = True
+                a.steps, a.warmup = min(args.steps, 5), 3
+                a.parity_frames = 8
+                run_ours(a)
     else:
         run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

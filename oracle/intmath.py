@@ -236,3 +236,83 @@ def dilate_square(img: np.ndarray, k: int) -> np.ndarray:
     for dy in range(k):
         out = np.maximum(out, rows[dy:dy + h, :])
     return out
+
+
+# ---- HashDetector pieces (hash_detector.py:124-158), restated from OpenCV 4.13's algorithms ----
+def bgr_to_gray(bgr: np.ndarray) -> np.ndarray:
+    """cv2.COLOR_BGR2GRAY for 8-bit: 15-bit fixed point (B 3735, G 19235, R 9798), not the 14-bit YUV-Y."""
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+
+
+def area_tab(ssize: int, dsize: int) -> list[tuple[int, int, np.float32]]:
+    """computeResizeAreaTab (imgproc/resize.cpp): (dst index, src index, float32 weight) in source order."""
+    import math
+    scale = ssize / dsize
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area(gray: np.ndarray, n: int) -> np.ndarray:
+    """cv2.resize(gray, (n, n), INTER_AREA) for a shrinking 8-bit image.  Integer scale factors take OpenCV's
+    integer-sum path (sum * float32(1/area), rounded; 2x2 is (sum + 2) >> 2); otherwise every destination cell
+    is a float32 accumulation `buf += S * alpha` per source row and `sum += beta * buf` down the rows, in source
+    order, separate multiply and add - the order matters for the last bit."""
+    H, W = gray.shape
+    if W % n == 0 and H % n == 0:
+        sx, sy = W // n, H // n
+        s = gray.astype(np.int64).reshape(n, sy, n, sx).sum(axis=(1, 3))
+        if sx == 2 and sy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        if sx == 1 and sy == 1:
+            return gray.copy()
+        return np.clip(np.rint(s.astype(np.float32) * np.float32(1.0 / (sx * sy))), 0, 255).astype(np.uint8)
+    xt, yt = area_tab(W, n), area_tab(H, n)
+    xi = np.array([t[0] for t in xt]); xs = np.array([t[1] for t in xt]); xa = np.array([t[2] for t in xt], np.float32)
+    S = gray.astype(np.float32)
+    out = np.zeros((n, n), np.uint8)
+    sumv = np.zeros(n, np.float32)
+    prev_dy = yt[0][0]
+    for dy, sy, beta in yt:
+        buf = np.zeros(n, np.float32)
+        prod = (S[sy, xs] * xa).astype(np.float32)
+        for k in range(len(xt)):                      # sequential float32 adds, source order
+            buf[xi[k]] = np.float32(buf[xi[k]] + prod[k])
+        if dy != prev_dy:
+            out[prev_dy] = np.clip(np.rint(sumv), 0, 255).astype(np.uint8)
+            sumv = (beta * buf).astype(np.float32)
+            prev_dy = dy
+        else:
+            sumv = (sumv + (beta * buf).astype(np.float32)).astype(np.float32)
+    out[prev_dy] = np.clip(np.rint(sumv), 0, 255).astype(np.uint8)
+    return out
+
+
+def phash_bits(bgr: np.ndarray, hash_size: int, factor: int) -> np.ndarray:
+    """hash_frame with the integer stages exact and the DCT in float64 (cv2.dct is float32 through IPP: a bit
+    can differ only where a coefficient sits within rounding distance of the median)."""
+    n = hash_size * factor
+    r = resize_area(bgr_to_gray(bgr), n)
+    mx = int(r.max()) or 1
+    x = (r.astype(np.float32) / np.float32(mx)).astype(np.float64)
+    k = np.arange(n)
+    C = np.cos(np.pi * (2 * k[None, :] + 1) * k[:, None] / (2 * n)) * np.sqrt(2.0 / n)
+    C[0, :] = np.sqrt(1.0 / n)
+    low = (C @ x @ C.T)[:hash_size, :hash_size].astype(np.float32)
+    flat = np.sort(low.ravel())
+    m = flat.size
+    med = flat[m // 2] if m % 2 else np.float32(np.float32(flat[m // 2 - 1] + flat[m // 2]) * np.float32(0.5))
+    return low > med

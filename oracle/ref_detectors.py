@@ -374,6 +374,62 @@ class RefHistogramDetector:
         return []
 
 
+def hash_frame(frame_img: numpy.ndarray, hash_size: int, factor: int) -> numpy.ndarray:
+    """hash_detector.py:124-158 (pHash: gray -> INTER_AREA square -> /max -> DCT -> low band > median)."""
+    gray_img = cv2.cvtColor(frame_img, cv2.COLOR_BGR2GRAY)
+    imsize = hash_size * factor
+    resized_img = cv2.resize(gray_img, (imsize, imsize), interpolation=cv2.INTER_AREA)
+    max_value = numpy.max(numpy.max(resized_img))
+    if max_value == 0:
+        max_value = 1
+    resized_img = numpy.asarray(numpy.float32(resized_img) / max_value)
+    dct_complete = cv2.dct(resized_img)
+    dct_low_freq = dct_complete[:hash_size, :hash_size]
+    med = numpy.median(numpy.asarray(dct_low_freq, dtype=numpy.float32))
+    return dct_low_freq > med
+
+
+class RefHashDetector:
+    """hash_detector.py:27-122."""
+
+    def __init__(self, threshold=0.35, size=8, lowpass=2, min_scene_len=15, fps=30.0, with_stats=False):
+        self._threshold = threshold
+        self._rate = _as_rate(fps)
+        self._min_scene_len = min_len_to_frames(min_scene_len, self._rate)
+        self._size = size
+        self._size_sq = float(size * size)
+        self._factor = lowpass
+        self._last_frame = None
+        self._last_scene_cut = None
+        self._last_hash = numpy.array([])
+        self.metric_key = f"hash_dist [size={size} lowpass={lowpass}]"
+        self.with_stats = with_stats
+        self.metrics: dict[int, dict] = {}
+
+    def process_frame(self, t: int, frame_img: numpy.ndarray) -> list[int]:
+        cuts = []
+        if self._last_scene_cut is None:
+            self._last_scene_cut = t
+        if self._last_frame is not None:
+            curr_hash = hash_frame(frame_img, self._size, self._factor)
+            last_hash = self._last_hash
+            if last_hash.size == 0:
+                last_hash = hash_frame(self._last_frame, self._size, self._factor)
+            hash_dist = numpy.count_nonzero(curr_hash.flatten() != last_hash.flatten())
+            hash_dist_norm = hash_dist / self._size_sq
+            if self.with_stats:
+                self.metrics.setdefault(t, {})[self.metric_key] = hash_dist_norm
+            self._last_hash = curr_hash
+            if hash_dist_norm >= self._threshold and max(0, t - self._last_scene_cut) >= self._min_scene_len:
+                cuts.append(t)
+                self._last_scene_cut = t
+        self._last_frame = frame_img.copy()
+        return cuts
+
+    def post_process(self, t: int) -> list[int]:
+        return []
+
+
 # --- SceneManager pieces on the path (scene_manager.py) -------------------------------------
 
 

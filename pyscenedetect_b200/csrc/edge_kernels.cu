@@ -74,6 +74,13 @@ __device__ __forceinline__ uint32_t canny_sector(int gx, int gy) {
     return ((gx ^ gy) < 0) ? 3u : 2u;
 }
 
+// sum of (unsigned byte of a) x (signed byte of b): the C++ __dp4a overloads are all-signed or all-unsigned
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
             const int b = 2 + i;
             const uint32_t t = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1 > 3 ? 3 : (b >> 2) + 1], 8 * (b & 3));
             h[i] = __dp4a(t, 0x00010201u, 0u);          // V(i-1) + 2 V(i) + V(i+1)
-            c[i] = __dp4a((int)t, (int)0x000100FF, 0);  // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
+            c[i] = dp4a_u8_s8(t, 0x000100FFu);          // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
         }
     };
     // gradient of row y from the sums of rows y-1 (a), y (b), y+1 (c): magnitudes of the 10 columns and the

@@ -348,7 +348,7 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 #define PSD_WS_WAITMODE 0  // 0: try_wait with a suspend-time hint, 1: plain try_wait, 2: test_wait first, then try_wait
 #endif
 #ifndef PSD_WS_PAIRWAIT
-#define PSD_WS_PAIRWAIT 0  // 1: the consumer checks the FULL barriers of two consecutive frames back to back
+#define PSD_WS_PAIRWAIT 1  // 1: the consumer checks the FULL barriers of two consecutive frames back to back
 #endif
 // try_wait with a long suspend-time hint: the waiting warp sleeps in hardware until the phase
 // completes instead of burning issue slots of its sub-partition in a poll loop

@@ -31,6 +31,7 @@ from scenedetect.detector import FlashFilter  # noqa: E402
 from scenedetect.detectors import (  # noqa: E402
     AdaptiveDetector,
     ContentDetector,
+    HashDetector,
     HistogramDetector,
     ThresholdDetector,
 )
@@ -87,6 +88,7 @@ DETECTORS = {
     "adaptive": AdaptiveDetector,
     "threshold": ThresholdDetector,
     "histogram": HistogramDetector,
+    "hash": HashDetector,
 }
 
 
@@ -166,6 +168,27 @@ CASES = [
 ]
 
 
+# Second fixture file (golden_v2.json): HashDetector and a histogram-through-SceneManager case
+# whose cut list is not empty (golden_v1's sm_hist_downscale3 has none).
+CASES_V2 = [
+    # 160x90 -> 16x16: non-integer area scale (10 x 5.625): OpenCV's float-accumulating INTER_AREA path
+    dict(name="hash_default", gen=(260, 160, 90, 0, 20, 70, 30), det="hash", kw={}, mode="direct", stats=True, fps=30.0),
+    # 256x144 -> 16x16: integer scale (16 x 9): the integer-sum path; lower threshold, float min_scene_len
+    dict(name="hash_int_scale", gen=(220, 256, 144, 5, 20, 60, 30), det="hash",
+         kw=dict(threshold=0.25, min_scene_len=0.4), mode="direct", stats=True, fps=25.0),
+    # size 16, lowpass 4 -> 64x64 DCT, 256-bit hash; 320x176 -> 64: scale 5 x 2.75
+    dict(name="hash_16_4", gen=(200, 320, 176, 6, 20, 60, 30), det="hash",
+         kw=dict(size=16, lowpass=4, threshold=0.3), mode="direct", stats=True, fps=30.0),
+    dict(name="hash_4_2_odd", gen=(160, 131, 97, 12, 20, 50, 30), det="hash",
+         kw=dict(size=4, lowpass=2, threshold=0.3, min_scene_len=10), mode="direct", stats=False, fps=30.0),
+    # through the reference SceneManager: 640x360 auto-downscaled to 256x144 first
+    dict(name="sm_hash_downscale", gen=(220, 640, 360, 12, 20, 70, 30), det="hash", kw={},
+         mode="scene_manager", stats=True, fps=30.0, auto_downscale=True),
+    dict(name="sm_hist_downscale2_cuts", gen=(260, 320, 180, 10, 20, 70, 30), det="histogram",
+         kw=dict(bins=256, threshold=0.05), mode="scene_manager", stats=True, fps=30.0, downscale=2),
+]
+
+
 def run_case(case: dict) -> dict:
     n, w, h, seed, mn, mx, ns = case["gen"]
     plan = ScenePlan(n, seed=seed, noise_shift=ns, min_len=mn, max_len=mx)
@@ -227,6 +250,13 @@ def main():
     with open(path, "w") as f:
         json.dump(golden, f, indent=0, sort_keys=True)
     for c in golden["cases"]:
+        print(c["name"], "cuts", c["cuts"], "true", c["true_cuts"])
+    print("wrote", path, os.path.getsize(path), "bytes")
+    golden2 = dict(golden, cases=[run_case(c) for c in CASES_V2])
+    path = os.path.join(HERE, "golden_v2.json")
+    with open(path, "w") as f:
+        json.dump(golden2, f, indent=0, sort_keys=True)
+    for c in golden2["cases"]:
         print(c["name"], "cuts", c["cuts"], "true", c["true_cuts"])
     print("wrote", path, os.path.getsize(path), "bytes")
 
