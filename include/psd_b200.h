@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary for the hot path named in BASELINE.json: the
  * process_frame() arithmetic of ContentDetector / AdaptiveDetector / ThresholdDetector /
- * HistogramDetector plus the cv2.resize pre-step SceneManager applies.  The reference is
+ * HistogramDetector / HashDetector plus the cv2.resize pre-step SceneManager applies.  The reference is
  * pure Python over cv2/numpy and has no FFI of its own, so every entry
  * point below replaces a cv2/numpy call sequence at the reference line cited; the Python
  * host (pyscenedetect_b200/_capi.py) binds them with ctypes.
@@ -38,6 +38,8 @@ extern "C" {
 #define PSD_F_BGRSUM 2u /* sum of all B,G,R bytes: numpy.mean(frame_img), threshold_detector.py:127 */
 #define PSD_F_YHIST 4u  /* 256-bin histogram of YUV-Y: histogram_detector.py:156-159 */
 #define PSD_F_EDGES 8u  /* Canny+dilate edge-map SAD: content_detector.py:213-239 (implies HSV) */
+#define PSD_F_HASH 16u  /* perceptual hash of every frame: hash_detector.py:124-158 */
+#define PSD_HASH_WORDS 4 /* a hash occupies 4 x uint64 (size * size <= 256 bits), bit u*size+v = D[u][v] > median */
 
 /* engine flags (psd_config.flags) */
 #define PSD_CFG_GENERIC_KERNEL 1u /* score every strip with the generic kernel instead of the persistent
@@ -61,7 +63,9 @@ typedef struct psd_config {
     int32_t edge_kernel_size; /* dilate kernel k (odd >= 3); 0 = content_detector.py:39-46 estimate */
     int32_t max_batch;        /* max frames per submit call (staging is sized for it) */
     uint32_t flags;           /* PSD_CFG_* */
-    int32_t reserved[6];
+    int32_t hash_size;        /* PSD_F_HASH: HashDetector(size=...), 0 = 8 */
+    int32_t hash_lowpass;     /* PSD_F_HASH: HashDetector(lowpass=...), 0 = 2 */
+    int32_t reserved[4];
 } psd_config;
 
 /* Per-frame integer results (device- and host-side layout, 64 bytes). */
@@ -123,8 +127,11 @@ int64_t psd_engine_frame_count(const psd_engine* e);
 /* copy results for frames [first, first+n) to host (implies sync) */
 int psd_engine_read_sums(psd_engine* e, int64_t first, int64_t n, psd_frame_sums* out);
 int psd_engine_read_yhist(psd_engine* e, int64_t first, int64_t n, uint32_t* out /*[n][256]*/);
+int psd_engine_read_hash(psd_engine* e, int64_t first, int64_t n, uint64_t* out /*[n][PSD_HASH_WORDS]*/);
 /* device pointers of the engine-owned result arrays (valid until destroy/reset) */
 int psd_engine_device_results(psd_engine* e, const psd_frame_sums** sums, const uint32_t** yhist);
+int psd_engine_device_hash(psd_engine* e, const uint64_t** hashes /* stream frame i at hashes + i*PSD_HASH_WORDS;
+                                                                      the halo frame's hash sits one entry before */);
 /* CUDA-event time (ms) spent in the engine's kernels between the first launch after the last
  * psd_engine_timing_reset() and the last launch (on the engine's compute stream). */
 int psd_engine_timing_reset(psd_engine* e);
@@ -155,6 +162,10 @@ int psd_scan_average(const psd_frame_sums* sums, int64_t n, int64_t n_values, do
  * array) uses prev_hist if non-NULL else is NaN. */
 int psd_scan_hist_correl(const uint32_t* yhist, int64_t n, int32_t bins, const uint32_t* prev_hist,
                          double* out_correl, void* stream);
+/* hash_detector.py:95-99: hash_dist = popcount(hash_t xor hash_{t-1}) / (size*size); out[0] uses prev_hash if
+ * non-NULL else is NaN */
+int psd_scan_hash_dist(const uint64_t* hashes, int64_t n, int32_t hash_size, const uint64_t* prev_hash,
+                       double* out_dist, void* stream);
 /* >= / <= compare producing u8 flags (content_detector.py:210, histogram_detector.py:108) */
 int psd_scan_compare(const double* values, int64_t n, double threshold, int32_t op /*0: >=, 1: <=, 2: <*/,
                      uint8_t* out_flags, void* stream);
@@ -172,6 +183,9 @@ int psd_cuts_adaptive(const double* ratio, const double* score, int64_t n, int64
 /* histogram_detector.py:87-112: cut where correl <= threshold and min_frames since the last cut */
 int psd_cuts_histogram(const double* correl, int64_t n, int64_t first_frame, double threshold,
                        int64_t min_frames, int64_t* cuts, int32_t* count, int32_t cap, void* stream);
+/* hash_detector.py:104-109: cut where dist >= threshold and min_frames since the last cut (NaN = no predecessor) */
+int psd_cuts_hash(const double* dist, int64_t n, int64_t first_frame, double threshold, int64_t min_frames,
+                  int64_t* cuts, int32_t* count, int32_t cap, void* stream);
 /* threshold_detector.py:113-191: fade in/out automaton incl. the post_process final cut */
 int psd_cuts_threshold(const double* average, int64_t n, int64_t first_frame, double threshold,
                        int32_t method_ceiling, double fade_bias, int64_t min_frames, int32_t add_final_scene,
@@ -186,6 +200,7 @@ int psd_engine_scan_adaptive_host(psd_engine* e, const double* scores_host, int6
 int psd_engine_scan_average_host(psd_engine* e, int64_t first, int64_t n, double* out_avg);
 int psd_engine_scan_hist_correl_host(psd_engine* e, int64_t first, int64_t n, int32_t bins,
                                      double* out_correl);
+int psd_engine_scan_hash_dist_host(psd_engine* e, int64_t first, int64_t n, double* out_dist);
 
 /* ---- synthetic input generator (bench.py / tests; pyscenedetect_b200/synth.py bit-exact twin) ---- */
 /* params_host: [n][24] int32 rows of ScenePlan.params for frames first..first+n-1 */

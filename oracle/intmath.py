@@ -279,7 +279,7 @@ def resize_area(gray: np.ndarray, n: int) -> np.ndarray:
             return ((s + 2) >> 2).astype(np.uint8)
         if sx == 1 and sy == 1:
             return gray.copy()
-        return np.clip(np.rint(s.astype(np.float32) * np.float32(1.0 / (sx * sy))), 0, 255).astype(np.uint8)
+        return np.clip(np.rint(s.astype(np.float32) * (np.float32(1.0) / np.float32(sx * sy))), 0, 255).astype(np.uint8)
     xt, yt = area_tab(W, n), area_tab(H, n)
     xi = np.array([t[0] for t in xt]); xs = np.array([t[1] for t in xt]); xa = np.array([t[2] for t in xt], np.float32)
     S = gray.astype(np.float32)

@@ -25,6 +25,8 @@ F_HSV = 1
 F_BGRSUM = 2
 F_YHIST = 4
 F_EDGES = 8
+F_HASH = 16
+HASH_WORDS = 4
 SUBMIT_PINNED = 1
 CFG_GENERIC_KERNEL = 1
 
@@ -41,7 +43,9 @@ class PsdConfig(C.Structure):
         ("edge_kernel_size", C.c_int32),
         ("max_batch", C.c_int32),
         ("flags", C.c_uint32),
-        ("reserved", C.c_int32 * 6),
+        ("hash_size", C.c_int32),
+        ("hash_lowpass", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -87,7 +91,9 @@ SIGNATURES = {
     "psd_engine_frame_count": (_i64, [_vp]),
     "psd_engine_read_sums": (C.c_int, [_vp, _i64, _i64, _vp]),
     "psd_engine_read_yhist": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "psd_engine_read_hash": (C.c_int, [_vp, _i64, _i64, _vp]),
     "psd_engine_device_results": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "psd_engine_device_hash": (C.c_int, [_vp, C.POINTER(_vp)]),
     "psd_engine_timing_reset": (C.c_int, [_vp]),
     "psd_engine_timing_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.POINTER(C.c_uint64)]),
@@ -97,15 +103,18 @@ SIGNATURES = {
     "psd_scan_adaptive": (C.c_int, [_vp, _i64, _i32, _dbl, _vp, _vp]),
     "psd_scan_average": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "psd_scan_hist_correl": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "psd_scan_hash_dist": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "psd_scan_compare": (C.c_int, [_vp, _i64, _dbl, _i32, _vp, _vp]),
     "psd_cuts_flash_filter": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
     "psd_cuts_adaptive": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _i64, _vp, _vp, _i32, _vp]),
     "psd_cuts_histogram": (C.c_int, [_vp, _i64, _i64, _dbl, _i64, _vp, _vp, _i32, _vp]),
+    "psd_cuts_hash": (C.c_int, [_vp, _i64, _i64, _dbl, _i64, _vp, _vp, _i32, _vp]),
     "psd_cuts_threshold": (C.c_int, [_vp, _i64, _i64, _dbl, _i32, _dbl, _i64, _i32, _vp, _vp, _i32, _vp]),
     "psd_engine_scan_content_host": (C.c_int, [_vp, _i64, _i64, _dp, _dbl, _vp, _vp]),
     "psd_engine_scan_adaptive_host": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "psd_engine_scan_average_host": (C.c_int, [_vp, _i64, _i64, _vp]),
     "psd_engine_scan_hist_correl_host": (C.c_int, [_vp, _i64, _i64, _i32, _vp]),
+    "psd_engine_scan_hash_dist_host": (C.c_int, [_vp, _i64, _i64, _vp]),
     "psd_synth_frames": (C.c_int, [C.c_int, _vp, _vp, _i64, _i32, _i32, _i64, _vp]),
     "psd_test_hsv": (C.c_int, [C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, C.c_int]),
 }

@@ -7,6 +7,7 @@
 //   psd_cuts_flash_filter   detector.py:160-224   (FlashFilter MERGE / SUPPRESS over score >= threshold)
 //   psd_cuts_adaptive       adaptive_detector.py:134-143
 //   psd_cuts_histogram      histogram_detector.py:87-112
+//   psd_cuts_hash           hash_detector.py:79-109
 //   psd_cuts_threshold      threshold_detector.py:113-168, 170-191
 #include "psd_common.cuh"
 
@@ -93,6 +94,23 @@ __global__ void psd_cuts_histogram_kernel(const double* __restrict__ correl, int
     }
 }
 
+__global__ void psd_cuts_hash_kernel(const double* __restrict__ dist, int64_t n, int64_t first_frame,
+                                     double threshold, int64_t min_frames, int64_t* cuts, int32_t* count,
+                                     int32_t cap) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    *count = 0;
+    int64_t last_cut = first_frame;  // hash_detector.py:79-80
+    for (int64_t i = 0; i < n; ++i) {
+        const double d = dist[i];
+        if (d != d) continue;         // NaN: no predecessor frame (hash_detector.py:83)
+        const int64_t t = first_frame + i;
+        if (d >= threshold && (t - last_cut) >= min_frames) {
+            push_cut(cuts, count, cap, t);
+            last_cut = t;
+        }
+    }
+}
+
 __global__ void psd_cuts_threshold_kernel(const double* __restrict__ avg, int64_t n, int64_t first_frame,
                                           double threshold, int method_ceiling, double fade_bias,
                                           int64_t min_frames, int add_final_scene, int64_t* cuts,
@@ -148,6 +166,15 @@ extern "C" int psd_cuts_adaptive(const double* ratio, const double* score, int64
     psd_cuts_adaptive_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ratio, score, n, first_frame, window_width,
                                                                  adaptive_threshold, min_content_val, min_frames,
                                                                  cuts, count, cap);
+    PSD_CHECK_LAUNCH();
+    count_launch();
+    return PSD_OK;
+}
+
+extern "C" int psd_cuts_hash(const double* dist, int64_t n, int64_t first_frame, double threshold,
+                             int64_t min_frames, int64_t* cuts, int32_t* count, int32_t cap, void* stream) {
+    CUT_ARGS_OK(dist);
+    psd_cuts_hash_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dist, n, first_frame, threshold, min_frames, cuts, count, cap);
     PSD_CHECK_LAUNCH();
     count_launch();
     return PSD_OK;

@@ -62,16 +62,15 @@ __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, i
 // state.  No shared memory, no shuffles, no barrier; neighbouring threads re-read overlapping words from L1.
 constexpr int kBandRows = 32;
 
-// direction sector of a pixel (OpenCV's fixed-point tangent test): 0 = compare left/right, 1 = up/down,
-// 2 = the (y-1,x-1)/(y+1,x+1) diagonal, 3 = the (y-1,x+1)/(y+1,x-1) diagonal
+// direction sector of a pixel (OpenCV's fixed-point tangent test), branch-free: 0 = compare left/right,
+// 1 = up/down, 2 = the (y-1,x-1)/(y+1,x+1) diagonal, 3 = the (y-1,x+1)/(y+1,x-1) diagonal
 __device__ __forceinline__ uint32_t canny_sector(int gx, int gy) {
     const int ax = abs(gx);
     const int ay = abs(gy) << 15;
     const int tg22x = ax * 13573;
     const int tg67x = tg22x + (ax << 16);
-    if (ay < tg22x) return 0u;
-    if (ay > tg67x) return 1u;
-    return ((gx ^ gy) < 0) ? 3u : 2u;
+    const uint32_t diag = ((gx ^ gy) < 0) ? 3u : 2u;
+    return (ay < tg22x) ? 0u : ((ay > tg67x) ? 1u : diag);
 }
 
 // sum of (unsigned byte of a) x (signed byte of b): the C++ __dp4a overloads are all-signed or all-unsigned
@@ -82,7 +81,7 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
+__global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
     uint32_t* __restrict__ cand_bits, int W, int H, int Wq, int strips, int bands, int64_t n_threads) {
     const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -104,11 +103,10 @@ __global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
     for (int i = 0; i < 10; ++i)
         if (x0 - 1 + i >= 0 && x0 - 1 + i < W) col_in |= 1u << i;
 
-    // horizontal sums of row y (BORDER_REPLICATE in both directions)
-    auto sums_of_row = [&](int y, int (&h)[10], int (&c)[10]) {
+    // the 16 bytes x0-4 .. x0+11 of row y (BORDER_REPLICATE in both directions)
+    auto load_window = [&](int y, uint32_t (&w)[4]) {
         const int yc = min(max(y, 0), H - 1);
         const uint8_t* row = src + (int64_t)yc * W;
-        uint32_t w[4];
         if (ALIGNED) {  // W % 8 == 0: every strip is whole, words are 4-byte aligned
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(row) + 2 * sx;
             w[1] = rw[0];
@@ -123,76 +121,78 @@ __global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
                 w[k >> 2] |= (uint32_t)row[x] << (8 * (k & 3));
             }
         }
-        // window bytes: w[0] = x0-4..x0-1, ..., w[3] = x0+8..x0+11; gradient column i is x0-1+i, its left
-        // neighbour is window byte 2+i
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const int b = 2 + i;
-            const uint32_t t = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1 > 3 ? 3 : (b >> 2) + 1], 8 * (b & 3));
-            h[i] = __dp4a(t, 0x00010201u, 0u);          // V(i-1) + 2 V(i) + V(i+1)
-            c[i] = dp4a_u8_s8(t, 0x000100FFu);          // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
-        }
     };
-    // gradient of row y from the sums of rows y-1 (a), y (b), y+1 (c): magnitudes of the 10 columns and the
-    // direction sectors of the 8 output columns that exceed the low threshold (2 bits each)
-    auto gradient = [&](int y, const int (&ca)[10], const int (&cb)[10], const int (&cc)[10], const int (&ha)[10],
-                        const int (&hc)[10], int (&m)[10], uint32_t& dir) {
-        const bool row_in = y >= 0 && y < H;
-        dir = 0;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const bool in = row_in && ((col_in >> i) & 1u);
-            const int gx = in ? ca[i] + 2 * cb[i] + cc[i] : 0;
-            const int gy = in ? hc[i] - ha[i] : 0;
-            m[i] = abs(gx) + abs(gy);
-            if (i >= 1 && i <= 8 && m[i] > low) dir |= canny_sector(gx, gy) << (2 * (i - 1));
-        }
+    // horizontal sums of gradient column i (x0-1+i) from a window: its left neighbour is window byte 2+i
+    auto col_sums = [&](const uint32_t (&w)[4], int i, int& h, int& c) {
+        const int b = 2 + i;
+        const uint32_t t = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1 > 3 ? 3 : (b >> 2) + 1], 8 * (b & 3));
+        h = __dp4a(t, 0x00010201u, 0u);   // V(i-1) + 2 V(i) + V(i+1)
+        c = dp4a_u8_s8(t, 0x000100FFu);   // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
     };
 
     int cA[10], cB[10], hA[10], hB[10];   // sums of the two most recent rows (roles alternate)
     int mU[10], mC[10], mD[10];           // magnitudes of rows y-1, y, y+1
-    uint32_t dirC, dirD;
+    uint32_t dirC = 0, dirD = 0;          // direction sectors of the 8 output columns (2 bits each), rows y, y+1
+    // Row `yy+1` arrives: gradient of row yy from rows yy-1 (`co`/`ho`, overwritten with row yy+1 on the way
+    // out), yy (`cm`) and yy+1.  Magnitudes go to `m`, sectors to `dir` (only if some pixel can be a candidate).
+    auto advance = [&](int yy, int (&co)[10], const int (&cm)[10], int (&ho)[10], int (&m)[10], uint32_t& dir) {
+        uint32_t w[4];
+        load_window(yy + 1, w);
+        const bool row_in = yy >= 0 && yy < H;
+        int gxs[8], gys[8];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            int hn, cn;
+            col_sums(w, i, hn, cn);
+            const bool in = row_in && ((col_in >> i) & 1u);
+            const int gx = in ? co[i] + 2 * cm[i] + cn : 0;
+            const int gy = in ? hn - ho[i] : 0;
+            co[i] = cn;
+            ho[i] = hn;
+            m[i] = abs(gx) + abs(gy);
+            if (i >= 1 && i <= 8) {
+                gxs[i - 1] = gx; gys[i - 1] = gy;
+                any |= m[i] > low;
+            }
+        }
+        dir = 0;
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dir |= canny_sector(gxs[i], gys[i]) << (2 * i);
+        }
+    };
+    // prologue: rows yb-2, yb-1 into (A, B); gradients of rows yb-1 and yb
     {
-        int h0[10], c0[10];
-        sums_of_row(yb - 2, h0, c0);
-        sums_of_row(yb - 1, hA, cA);
-        sums_of_row(yb, hB, cB);
+        uint32_t w[4];
+        load_window(yb - 2, w);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) col_sums(w, i, hA[i], cA[i]);
+        load_window(yb - 1, w);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) col_sums(w, i, hB[i], cB[i]);
         uint32_t unused;
-        gradient(yb - 1, c0, cA, cB, h0, hB, mU, unused);
-        // rows yb-1 (A), yb (B) -> gradient of yb needs row yb+1
-        int h2[10], c2[10];
-        sums_of_row(yb + 1, h2, c2);
-        gradient(yb, cA, cB, c2, hA, h2, mC, dirC);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) { cA[i] = cB[i]; hA[i] = hB[i]; cB[i] = c2[i]; hB[i] = h2[i]; }
+        advance(yb - 1, cA, cB, hA, mU, unused);   // A: yb-2 -> yb
+        advance(yb, cB, cA, hB, mC, dirC);         // B: yb-1 -> yb+1
     }
-    // one output row: `co`/`ho` hold row y, `cm`/`hm` row y+1; they leave holding row y+2 / row y+1
-    auto row_step = [&](int y, int (&co)[10], int (&cm)[10], int (&ho)[10], int (&hm)[10]) {
-        int hn[10], cn[10];
-        sums_of_row(y + 2, hn, cn);
-        gradient(y + 1, co, cm, cn, ho, hn, mD, dirD);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) { co[i] = cn[i]; ho[i] = hn[i]; }
+    // one output row y: on entry (co, ho) hold row y, (cm) row y+1
+    auto row_step = [&](int y, int (&co)[10], const int (&cm)[10], int (&ho)[10]) {
+        advance(y + 1, co, cm, ho, mD, dirD);
         uint32_t ebyte = 0, cbyte = 0;
         bool any = false;
 #pragma unroll
         for (int i = 1; i <= 8; ++i) any |= mC[i] > low;
         if (any) {
 #pragma unroll
-            for (int i = 1; i <= 8; ++i) {  // output column x0 + i - 1
+            for (int i = 1; i <= 8; ++i) {  // output column x0 + i - 1; every choice is a select, no branches
                 const int m = mC[i];
-                if (m > low && ((col_in >> i) & 1u)) {
-                    const uint32_t d = (dirC >> (2 * (i - 1))) & 3u;
-                    bool keep;
-                    if (d == 0u) keep = (m > mC[i - 1]) && (m >= mC[i + 1]);
-                    else if (d == 1u) keep = (m > mU[i]) && (m >= mD[i]);
-                    else if (d == 2u) keep = (m > mU[i - 1]) && (m > mD[i + 1]);
-                    else keep = (m > mU[i + 1]) && (m > mD[i - 1]);
-                    if (keep) {
-                        cbyte |= 1u << (i - 1);
-                        if (m > high) ebyte |= 1u << (i - 1);
-                    }
-                }
+                const uint32_t d = (dirC >> (2 * (i - 1))) & 3u;
+                const int n1 = d == 0u ? mC[i - 1] : d == 1u ? mU[i] : d == 2u ? mU[i - 1] : mU[i + 1];
+                const int n2 = d == 0u ? mC[i + 1] : d == 1u ? mD[i] : d == 2u ? mD[i + 1] : mD[i - 1];
+                // sectors 0 and 1 keep the pixel on "m >= second neighbour", the diagonals need "m >"
+                const bool keep = (m > low) && (m > n1) && (m + (d < 2u ? 1 : 0) > n2) && ((col_in >> i) & 1u);
+                cbyte |= keep ? (1u << (i - 1)) : 0u;
+                ebyte |= (keep && m > high) ? (1u << (i - 1)) : 0u;
             }
         }
         eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
@@ -201,10 +201,11 @@ __global__ void __launch_bounds__(256) psd_canny_classify_bits_kernel(
         for (int i = 0; i < 10; ++i) { mU[i] = mC[i]; mC[i] = mD[i]; }
         dirC = dirD;
     };
+    // after the prologue: A holds row yb, B row yb+1
 #pragma unroll 1
     for (int y = yb; y < ye; y += 2) {
-        row_step(y, cA, cB, hA, hB);
-        if (y + 1 < ye) row_step(y + 1, cB, cA, hB, hA);
+        row_step(y, cA, cB, hA);
+        if (y + 1 < ye) row_step(y + 1, cB, cA, hB);
     }
 }
 

@@ -70,6 +70,8 @@ struct psd_engine {
     // results: slot 0 = halo frame, stream frame i at slot i+1
     psd_frame_sums* d_sums = nullptr;
     uint32_t* d_yhist = nullptr;
+    uint64_t* d_hash = nullptr;   // [capacity][PSD_HASH_WORDS]
+    HashPlan hash{};
     int64_t capacity = 0;
     int64_t n_frames = 0;
     bool halo_scored = false;
@@ -110,6 +112,18 @@ static int ensure_capacity(psd_engine* e, int64_t need_slots) {
             cudaFree(e->d_yhist);
         }
         e->d_yhist = nh;
+    }
+    if (e->features & PSD_F_HASH) {
+        uint64_t* nh = nullptr;
+        PSD_CUDA(cudaMalloc(&nh, (size_t)cap * PSD_HASH_WORDS * sizeof(uint64_t)));
+        PSD_CUDA(cudaMemsetAsync(nh, 0, (size_t)cap * PSD_HASH_WORDS * sizeof(uint64_t), e->compute_stream));
+        if (e->d_hash) {
+            PSD_CUDA(cudaMemcpyAsync(nh, e->d_hash, (size_t)(e->n_frames + 1) * PSD_HASH_WORDS * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToDevice, e->compute_stream));
+            PSD_CUDA(cudaStreamSynchronize(e->compute_stream));
+            cudaFree(e->d_hash);
+        }
+        e->d_hash = nh;
     }
     e->capacity = cap;
     return PSD_OK;
@@ -159,8 +173,15 @@ static int run_batch(psd_engine* e, const uint8_t* src, int64_t src_frame_stride
     a.vhist = (e->features & PSD_F_EDGES) ? e->eb.vhist : nullptr;
     a.vplane = (e->features & PSD_F_EDGES) ? e->eb.vplane : nullptr;
     PSD_CUDA(cudaEventRecord(k0, st));
-    int rc = launch_score(a, e->features, e->generic_only, st);
-    if (rc) return rc;
+    int rc = PSD_OK;
+    if (e->features & 15u) {  // the fused pass (HSV / byte sum / Y histogram / edges)
+        rc = launch_score(a, e->features & 15u, e->generic_only, st);
+        if (rc) return rc;
+    }
+    if (e->features & PSD_F_HASH) {
+        rc = launch_hash(e->hash, scored, scored_stride, (int)n, e->W, e->H, e->d_hash + slot0 * PSD_HASH_WORDS, st);
+        if (rc) return rc;
+    }
     PSD_CUDA(cudaEventRecord(k1, st));
     e->ev_score.push_back({k0, k1});
     if (e->features & PSD_F_EDGES) {
@@ -253,7 +274,8 @@ void psd_engine_destroy(psd_engine* e) {
         if (e->h2d_done[s]) cudaEventDestroy(e->h2d_done[s]);
     }
     cudaFree(e->small); cudaFree(e->d_xofs); cudaFree(e->d_xa); cudaFree(e->d_yofs); cudaFree(e->d_ya);
-    cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist);
+    cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist); cudaFree(e->d_hash);
+    hash_plan_destroy(&e->hash);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.cand);
     cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
     cudaFree(e->eb.carry_bits); cudaFree(e->eb.dirty); cudaFree(e->eb.hyst_flags);
@@ -280,7 +302,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
     PSD_REQUIRE(cfg->src_width > 0 && cfg->src_height > 0 && cfg->width > 0 && cfg->height > 0,
                 "frame sizes must be positive");
     PSD_REQUIRE((int64_t)cfg->src_width * cfg->src_height < (1LL << 30), "frame too large");
-    PSD_REQUIRE(cfg->features != 0 && (cfg->features & ~15u) == 0, "bad feature mask 0x%x", cfg->features);
+    PSD_REQUIRE(cfg->features != 0 && (cfg->features & ~31u) == 0, "bad feature mask 0x%x", cfg->features);
     PSD_REQUIRE(cfg->max_batch >= 1 && cfg->max_batch <= 4096, "max_batch must be in [1,4096]");
     PSD_REQUIRE(cfg->edge_kernel_size == 0 || (cfg->edge_kernel_size >= 3 && (cfg->edge_kernel_size & 1)),
                 "kernel_size must be odd integer >= 3");
@@ -318,6 +340,11 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
             if ((k & 1) == 0) k += 1;
         }
         e->ksize = k;
+    }
+    if (e->features & PSD_F_HASH) {
+        int rc = hash_plan_create(&e->hash, e->W, e->H, cfg->hash_size ? cfg->hash_size : 8,
+                                  cfg->hash_lowpass ? cfg->hash_lowpass : 2, e->max_batch);
+        if (rc) { psd_engine_destroy(e); return rc; }
     }
     ENG_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     ENG_CUDA(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
@@ -531,6 +558,22 @@ int psd_engine_read_yhist(psd_engine* e, int64_t first, int64_t n, uint32_t* out
     return PSD_OK;
 }
 
+int psd_engine_read_hash(psd_engine* e, int64_t first, int64_t n, uint64_t* out) {
+    PSD_REQUIRE(e && out, "psd_engine_read_hash: null argument");
+    PSD_REQUIRE(e->features & PSD_F_HASH, "engine was created without PSD_F_HASH");
+    PSD_REQUIRE(first >= -1 && n >= 0 && first + n <= e->n_frames, "frame range out of bounds");
+    int rc = psd_engine_sync(e);
+    if (rc) return rc;
+    if (n) PSD_CUDA(cudaMemcpy(out, e->d_hash + (first + 1) * PSD_HASH_WORDS, (size_t)n * PSD_HASH_WORDS * 8, cudaMemcpyDeviceToHost));
+    return PSD_OK;
+}
+
+int psd_engine_device_hash(psd_engine* e, const uint64_t** hashes) {
+    PSD_REQUIRE(e && hashes, "psd_engine_device_hash: null argument");
+    *hashes = e->d_hash ? e->d_hash + PSD_HASH_WORDS : nullptr;
+    return PSD_OK;
+}
+
 int psd_engine_device_results(psd_engine* e, const psd_frame_sums** sums, const uint32_t** yhist) {
     PSD_REQUIRE(e, "null engine");
     if (sums) *sums = e->d_sums + 1;
@@ -648,6 +691,28 @@ int psd_engine_scan_hist_correl_host(psd_engine* e, int64_t first, int64_t n, in
     // slot `first` (= stream frame first-1, or the halo slot) precedes slot first+1
     const uint32_t* prev = (first > 0 || e->halo_scored) ? e->d_yhist + first * 256 : nullptr;
     int rc = psd_scan_hist_correl(e->d_yhist + (first + 1) * 256, n, bins, prev, tmp, e->compute_stream);
+    if (!rc) rc = scan_to_host(e, tmp, out, (size_t)n);
+    cudaFree(tmp);
+    return rc;
+}
+
+int psd_scan_hash_dist(const uint64_t* hashes, int64_t n, int32_t hash_size, const uint64_t* prev_hash, double* out,
+                       void* stream) {
+    PSD_REQUIRE(hashes && out && n >= 0 && hash_size >= 1 && hash_size <= 16, "psd_scan_hash_dist: bad arguments");
+    return launch_hash_dist(hashes, n, hash_size, prev_hash, out, (cudaStream_t)stream);
+}
+
+int psd_engine_scan_hash_dist_host(psd_engine* e, int64_t first, int64_t n, double* out) {
+    PSD_REQUIRE(e && out, "psd_engine_scan_hash_dist_host: null argument");
+    PSD_REQUIRE(e->features & PSD_F_HASH, "engine was created without PSD_F_HASH");
+    PSD_REQUIRE(first >= 0 && n >= 0 && first + n <= e->n_frames, "frame range out of bounds");
+    if (n == 0) return PSD_OK;
+    PSD_CUDA(cudaSetDevice(e->device));
+    double* tmp = nullptr;
+    PSD_CUDA(cudaMalloc(&tmp, (size_t)n * sizeof(double)));
+    // slot `first` (= stream frame first-1, or the halo slot) precedes slot first+1
+    const uint64_t* prev = (first > 0 || e->halo_scored) ? e->d_hash + first * PSD_HASH_WORDS : nullptr;
+    int rc = psd_scan_hash_dist(e->d_hash + (first + 1) * PSD_HASH_WORDS, n, e->hash.size, prev, tmp, e->compute_stream);
     if (!rc) rc = scan_to_host(e, tmp, out, (size_t)n);
     cudaFree(tmp);
     return rc;

@@ -96,6 +96,23 @@ int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, 
                  psd_frame_sums* sums, cudaStream_t stream);
 int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, cudaStream_t stream);
 
+// ---- perceptual hash (hash_kernels.cu) ----
+struct HashPlan {        // per-engine tables for one (frame size, hash size, lowpass)
+    int n = 0, size = 0; // hash image edge (size * lowpass), low band edge
+    int fast = 0;        // both area scale factors are integers
+    int area_w = 0, area_h = 0;
+    int32_t *xstart = nullptr, *xsi = nullptr, *ystart = nullptr, *ysi = nullptr;
+    float *xalpha = nullptr, *ybeta = nullptr;
+    double* cosn = nullptr;   // [size][n] DCT-II basis rows
+    float* rowbuf = nullptr;  // [max_batch][H][n] horizontal pass
+};
+int hash_plan_create(HashPlan* p, int W, int H, int size, int lowpass, int max_batch);
+void hash_plan_destroy(HashPlan* p);
+int launch_hash(const HashPlan& p, const uint8_t* frames, int64_t frame_stride, int n_frames, int W, int H,
+                uint64_t* hashes, cudaStream_t stream);
+int launch_hash_dist(const uint64_t* hashes, int64_t n, int size, const uint64_t* prev_hash, double* out,
+                     cudaStream_t stream);
+
 // ---- synthetic generator (synth_kernel.cu) ----
 int launch_synth(uint8_t* out, const int32_t* d_params, int64_t n, int width, int height,
                  int64_t frame_stride, cudaStream_t stream);

@@ -37,6 +37,10 @@ class EngineDetector(SceneDetector):
     def edge_kernel_size_arg(self) -> int:
         return 0
 
+    def engine_kwargs(self) -> dict:
+        """Extra `Engine(...)` arguments this detector needs (e.g. the hash geometry)."""
+        return {}
+
     def configure(self, device: int = 0, max_batch: int = 64,
                   scored_size: tuple[int, int] | None = None) -> None:
         """Select device / batch size / on-device downscale target before the first frame."""
@@ -56,7 +60,7 @@ class EngineDetector(SceneDetector):
             sw, sh = self._scored_size if self._scored_size else (w, h)
             self._engine = Engine(w, h, self.required_features(), width=sw, height=sh,
                                   device=self._device, max_batch=self._max_batch,
-                                  edge_kernel_size=self.edge_kernel_size_arg())
+                                  edge_kernel_size=self.edge_kernel_size_arg(), **self.engine_kwargs())
             self._owns_engine = True
             self._base_index = 0
         return self._engine

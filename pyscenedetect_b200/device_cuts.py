@@ -119,6 +119,15 @@ class DeviceCuts:
                                            self._cap, self._stream), "psd_cuts_histogram")
         return self._fetch()
 
+    def hash(self, threshold=0.35, min_scene_len=15, fps=30.0, first_frame: int = 0) -> list[int]:
+        n = self._e.frame_count
+        hashes = self._e.device_hash()
+        dist = self._tmp(n)
+        check(self._lib.psd_scan_hash_dist(hashes, n, int(self._e.hash_size), None, dist.ptr, self._stream))
+        check(self._lib.psd_cuts_hash(dist.ptr, n, first_frame, float(threshold), min_len_frames(min_scene_len, fps),
+                                      self._cuts.ptr, self._count.ptr, self._cap, self._stream), "psd_cuts_hash")
+        return self._fetch()
+
     def threshold(self, threshold=12, min_scene_len=15, fade_bias=0.0, add_final_scene=False,
                   ceiling: bool = False, fps=30.0, first_frame: int = 0) -> list[int]:
         n = self._e.frame_count
@@ -136,7 +145,9 @@ def cuts_for_detector(dc: DeviceCuts, detector, fps, first_frame: int = 0) -> li
     """Run the device automaton that corresponds to a (fresh) detector object of this package with the
     detector's own parameters: the cut list its per-frame `process_frame` + `post_process` would produce."""
     from .compat import FlashFilter
-    from .detectors import AdaptiveDetector, ContentDetector, HistogramDetector, ThresholdDetector
+    from .detectors import AdaptiveDetector, ContentDetector, HashDetector, HistogramDetector, ThresholdDetector
+    if isinstance(detector, HashDetector):
+        return dc.hash(detector._threshold, detector._min_scene_len, fps, first_frame)
     if isinstance(detector, AdaptiveDetector):
         return dc.adaptive(tuple(detector._weights), detector.adaptive_threshold, detector.min_scene_len,
                            detector.window_width, detector.min_content_val, fps, first_frame)

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, SUMS_DTYPE, check
+from ._capi import F_BGRSUM, F_EDGES, F_HASH, F_HSV, F_YHIST, HASH_WORDS, SUMS_DTYPE, check
 
 
 class PinnedBuffer:
@@ -75,7 +75,8 @@ class Engine:
 
     def __init__(self, src_width: int, src_height: int, features: int, width: int | None = None,
                  height: int | None = None, device: int = 0, max_batch: int = 64,
-                 edge_kernel_size: int = 0, generic_kernel: bool = False):
+                 edge_kernel_size: int = 0, generic_kernel: bool = False, hash_size: int = 8,
+                 hash_lowpass: int = 2):
         self._lib = _capi.load()
         cfg = _capi.PsdConfig()
         cfg.struct_size = C.sizeof(_capi.PsdConfig)
@@ -87,6 +88,8 @@ class Engine:
         cfg.edge_kernel_size = int(edge_kernel_size)
         cfg.max_batch = int(max_batch)
         cfg.flags = _capi.CFG_GENERIC_KERNEL if generic_kernel else 0  # cross-check switch (tests)
+        cfg.hash_size, cfg.hash_lowpass = int(hash_size), int(hash_lowpass)
+        self.hash_size = int(hash_size)
         h = C.c_void_p()
         check(self._lib.psd_engine_create(C.byref(cfg), C.byref(h)), "psd_engine_create")
         self._h = h
@@ -180,6 +183,18 @@ class Engine:
         check(self._lib.psd_engine_read_yhist(self._h, first, n, out.ctypes.data), "psd_engine_read_yhist")
         return out
 
+    def read_hash(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """-> (n, 4) uint64: bit u*size+v of the 256-bit word = DCT[u][v] > median (hash_detector.py:156)."""
+        n = self.frame_count - first if n is None else n
+        out = np.zeros((n, HASH_WORDS), dtype=np.uint64)
+        check(self._lib.psd_engine_read_hash(self._h, first, n, out.ctypes.data), "psd_engine_read_hash")
+        return out
+
+    def device_hash(self) -> int | None:
+        p = C.c_void_p()
+        check(self._lib.psd_engine_device_hash(self._h, C.byref(p)))
+        return p.value
+
     def device_results(self) -> tuple[int, int | None]:
         s, h = C.c_void_p(), C.c_void_p()
         check(self._lib.psd_engine_device_results(self._h, C.byref(s), C.byref(h)))
@@ -218,6 +233,14 @@ class Engine:
         out = np.zeros(n, dtype=np.float64)
         check(self._lib.psd_engine_scan_hist_correl_host(self._h, first, n, int(bins), out.ctypes.data),
               "psd_engine_scan_hist_correl_host")
+        return out
+
+    def scan_hash_dist(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """hash_dist of frames [first, first+n) against their predecessors; NaN where there is none."""
+        n = self.frame_count - first if n is None else n
+        out = np.zeros(n, dtype=np.float64)
+        check(self._lib.psd_engine_scan_hash_dist_host(self._h, first, n, out.ctypes.data),
+              "psd_engine_scan_hash_dist_host")
         return out
 
     # -- instrumentation --
@@ -280,4 +303,4 @@ def synth_frames_device(dptr: int, params: np.ndarray, width: int, height: int,
 
 
 __all__ = ["Engine", "PinnedBuffer", "DeviceBuffer", "synth_frames_device", "bind_host_to_gpu_numa_node", "F_HSV", "F_BGRSUM",
-           "F_YHIST", "F_EDGES"]
+           "F_YHIST", "F_EDGES", "F_HASH"]

@@ -202,8 +202,13 @@ class SceneManager:
         ks = {d.edge_kernel_size_arg() for d in self._detector_list if d.required_features() & F_EDGES}
         if len(ks) > 1:
             raise ValueError("detectors sharing a SceneManager's fused pass must agree on kernel_size")
+        extra: dict = {}
+        for d in self._detector_list:
+            for k, v in d.engine_kwargs().items():
+                if extra.setdefault(k, v) != v:
+                    raise ValueError(f"detectors sharing a SceneManager's fused pass must agree on {k}")
         self._engine = Engine(w, h, features, width=sw, height=sh, device=self._device,
-                              max_batch=self._batch_size, edge_kernel_size=ks.pop() if ks else 0)
+                              max_batch=self._batch_size, edge_kernel_size=ks.pop() if ks else 0, **extra)
         for d in self._detector_list:
             d.attach_engine(self._engine)
         fps = video.frame_rate

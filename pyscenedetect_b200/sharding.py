@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._capi import F_YHIST, SUMS_DTYPE
+from ._capi import F_HASH, F_YHIST, HASH_WORDS, SUMS_DTYPE
 
 
 def shard_bounds(n_frames: int, world: int) -> list[int]:
@@ -85,7 +85,8 @@ class GatheredResults:
     """Scan provider over gathered integer results: presents the `Engine.scan_*` interface the
     detectors consume, backed by the stateless device scans of the C-ABI (psd_scan_*)."""
 
-    def __init__(self, sums: np.ndarray, yhist: np.ndarray | None, n_pixels: int, device: int = 0):
+    def __init__(self, sums: np.ndarray, yhist: np.ndarray | None, n_pixels: int, device: int = 0,
+                 hashes: np.ndarray | None = None, hash_size: int = 8, hash_lowpass: int = 2):
         import ctypes as C
 
         from . import _capi
@@ -101,6 +102,11 @@ class GatheredResults:
         if yhist is not None:
             self._hist = DeviceBuffer(max(1, yhist.nbytes), device)
             self._hist.upload(np.ascontiguousarray(yhist).view(np.uint8).reshape(-1))
+        self._hashes = None
+        self.hash_size = int(hash_size)
+        if hashes is not None:
+            self._hashes = DeviceBuffer(max(1, hashes.nbytes), device)
+            self._hashes.upload(np.ascontiguousarray(hashes).view(np.uint8).reshape(-1))
         self._DeviceBuffer = DeviceBuffer
 
     @property
@@ -112,6 +118,9 @@ class GatheredResults:
 
     def device_results(self):
         return self._sums.ptr, (self._hist.ptr if self._hist is not None else None)
+
+    def device_hash(self):
+        return self._hashes.ptr if self._hashes is not None else None
 
     def sync(self):
         pass
@@ -145,6 +154,14 @@ class GatheredResults:
         out = self._out(n)
         self._capi.check(self._lib.psd_scan_average(self._sums.ptr + first * 64, n, self.n_pixels * 3,
                                                     out.ptr, None), "psd_scan_average")
+        return self._fetch(out, n)
+
+    def scan_hash_dist(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self._n - first if n is None else n
+        out = self._out(n)
+        prev = self._hashes.ptr + (first - 1) * 8 * HASH_WORDS if first > 0 else None
+        self._capi.check(self._lib.psd_scan_hash_dist(self._hashes.ptr + first * 8 * HASH_WORDS, n, self.hash_size,
+                                                      prev, out.ptr, None), "psd_scan_hash_dist")
         return self._fetch(out, n)
 
     def scan_hist_correl(self, bins: int, first: int = 0, n: int | None = None) -> np.ndarray:
@@ -187,7 +204,7 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
     n_local = ring if n_local is None else int(n_local)
     features = detector.required_features()
     eng = engine_factory(w, h, features, device=device, max_batch=batch_size,
-                         edge_kernel_size=detector.edge_kernel_size_arg())
+                         edge_kernel_size=detector.edge_kernel_size_arg(), **detector.engine_kwargs())
     halo = comm.exchange_halo(frames_local[(n_local - 1) % ring] if n_local else None, (h, w, 3))
     if halo is not None:
         if isinstance(halo, np.ndarray):
@@ -203,12 +220,14 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
         i += k
     sums = eng.read_sums()
     yh = eng.read_yhist() if features & F_YHIST else None
+    hs = eng.read_hash() if features & F_HASH else None
     t_score = time.perf_counter()
     counts = [b - a for a, b in zip(shard_bounds(total_frames, comm.world)[:-1],
                                     shard_bounds(total_frames, comm.world)[1:])]
     assert counts[comm.rank] == n_local and shard_bounds(total_frames, comm.world)[comm.rank] == first_index
     all_sums = comm.gather_rows(sums, counts)
     all_hist = comm.gather_rows(yh, counts) if yh is not None else None
+    all_hash = comm.gather_rows(hs, counts) if hs is not None else None
     eng.close()
     t_gather = time.perf_counter()
 
@@ -220,7 +239,8 @@ def detect_sharded(frames_local: np.ndarray, first_index: int, total_frames: int
         note(t_gather)
         return None, None
     assert all_sums.dtype == SUMS_DTYPE and all_sums.shape[0] == total_frames
-    res = results_factory(all_sums, all_hist, w * h, device)
+    res = (results_factory(all_sums, all_hist, w * h, device, hashes=all_hash, **detector.engine_kwargs())
+           if all_hash is not None else results_factory(all_sums, all_hist, w * h, device))
     if detector.stats_manager is None and hasattr(res, "device_results"):
         from .device_cuts import DeviceCuts, cuts_for_detector
         cut_frames = sorted(set(cuts_for_detector(DeviceCuts(res), detector, fps)))

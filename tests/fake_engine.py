@@ -9,12 +9,12 @@ import numpy as np
 
 from oracle import intmath as M
 from oracle import ref_detectors as R
-from pyscenedetect_b200._capi import F_BGRSUM, F_EDGES, F_HSV, F_YHIST, SUMS_DTYPE
+from pyscenedetect_b200._capi import F_BGRSUM, F_EDGES, F_HASH, F_HSV, F_YHIST, SUMS_DTYPE
 
 
 class OracleEngine:
     def __init__(self, src_width, src_height, features, width=None, height=None, device=0,
-                 max_batch=64, edge_kernel_size=0, generic_kernel=False):
+                 max_batch=64, edge_kernel_size=0, generic_kernel=False, hash_size=8, hash_lowpass=2):
         self.src_width, self.src_height = src_width, src_height
         self.width = width if width is not None else src_width
         self.height = height if height is not None else src_height
@@ -23,6 +23,7 @@ class OracleEngine:
         self.max_batch = max_batch
         k = edge_kernel_size or R.estimated_kernel_size(self.width, self.height)
         self._kernel = np.ones((k, k), np.uint8)
+        self.hash_size, self.hash_lowpass = hash_size, hash_lowpass
         self.reset()
 
     def reset(self):
@@ -30,6 +31,8 @@ class OracleEngine:
         self._hist = []
         self._prev = None
         self._halo_hist = None
+        self._hashes = []
+        self._halo_hash = None
 
     @property
     def frame_count(self):
@@ -52,12 +55,15 @@ class OracleEngine:
         if self.features & F_BGRSUM:
             row["bgr_sum"] = int(frame.astype(np.int64).sum())
         hist = np.bincount(M.bgr_to_y(frame).ravel(), minlength=256).astype(np.uint32)
+        hbits = M.phash_bits(frame, self.hash_size, self.hash_lowpass) if self.features & F_HASH else None
         self._prev = (h, s, v, edges)
         if record:
             self._sums.append(row)
             self._hist.append(hist)
+            self._hashes.append(hbits)
         else:
             self._halo_hist = hist
+            self._halo_hash = hbits
 
     def set_halo(self, frame):
         assert self.frame_count == 0
@@ -82,6 +88,16 @@ class OracleEngine:
     def read_yhist(self, first=0, n=None):
         n = self.frame_count - first if n is None else n
         return np.array(self._hist[first:first + n], dtype=np.uint32).reshape(n, 256)
+
+    def read_hash(self, first=0, n=None):
+        """(n, 4) uint64 in the engine's bit order (bit u*size+v)"""
+        n = self.frame_count - first if n is None else n
+        out = np.zeros((n, 4), dtype=np.uint64)
+        for i in range(n):
+            flat = self._hashes[first + i].ravel()
+            for k in np.flatnonzero(flat):
+                out[i, k >> 6] |= np.uint64(1) << np.uint64(k & 63)
+        return out
 
     # scans: the reference's float64 operation order
     def scan_content(self, weights, first=0, n=None):
@@ -113,6 +129,16 @@ class OracleEngine:
         s = self.read_sums(first, n)
         return np.array([np.float64(int(r["bgr_sum"])) / float(self.n_pixels * 3) for r in s])
 
+    def scan_hash_dist(self, first=0, n=None):
+        n = self.frame_count - first if n is None else n
+        out = np.full(n, np.nan)
+        for i in range(n):
+            t = first + i
+            prev = self._hashes[t - 1] if t > 0 else self._halo_hash
+            if prev is not None:
+                out[i] = np.count_nonzero(self._hashes[t] != prev) / float(self.hash_size * self.hash_size)
+        return out
+
     def scan_hist_correl(self, bins, first=0, n=None):
         n = self.frame_count - first if n is None else n
         out = np.full(n, np.nan)
@@ -133,11 +159,19 @@ class OracleEngine:
 class OracleResults(OracleEngine):
     """`GatheredResults` stand-in: the scans of OracleEngine over gathered integer arrays."""
 
-    def __init__(self, sums, yhist, n_pixels, device=0):
+    def __init__(self, sums, yhist, n_pixels, device=0, hashes=None, hash_size=8, hash_lowpass=2):
         self.n_pixels = int(n_pixels)
         self._sums = list(sums)
         self._hist = list(yhist) if yhist is not None else []
         self._halo_hist = None
+        self.hash_size, self.hash_lowpass = hash_size, hash_lowpass
+        self._halo_hash = None
+        self._hashes = []
+        if hashes is not None:
+            m = hash_size * hash_size
+            for row in np.asarray(hashes, dtype=np.uint64):
+                bits = np.array([(int(row[k >> 6]) >> (k & 63)) & 1 for k in range(m)], dtype=bool)
+                self._hashes.append(bits.reshape(hash_size, hash_size))
 
     def read_sums(self, first=0, n=None):
         n = self.frame_count - first if n is None else n

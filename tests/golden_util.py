@@ -12,6 +12,7 @@ from pyscenedetect_b200.synth import ScenePlan, render_frames
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN_PATH = os.path.join(HERE, "golden", "golden_v1.json")
+GOLDEN_V2_PATH = os.path.join(HERE, "golden", "golden_v2.json")  # HashDetector + a histogram SceneManager case with cuts
 
 _cache: dict = {}
 
@@ -23,12 +24,21 @@ def load_golden() -> dict:
     return _cache["g"]
 
 
-def case_names() -> list[str]:
-    return [c["name"] for c in load_golden()["cases"]]
+def load_golden_v2() -> dict:
+    if "g2" not in _cache:
+        with open(GOLDEN_V2_PATH) as f:
+            _cache["g2"] = json.load(f)
+    return _cache["g2"]
+
+
+def case_names(which: str = "all") -> list[str]:
+    v1 = [c["name"] for c in load_golden()["cases"]]
+    v2 = [c["name"] for c in load_golden_v2()["cases"]]
+    return {"v1": v1, "v2": v2, "all": v1 + v2}[which]
 
 
 def get_case(name: str) -> dict:
-    for c in load_golden()["cases"]:
+    for c in load_golden()["cases"] + load_golden_v2()["cases"]:
         if c["name"] == name:
             return c
     raise KeyError(name)

@@ -27,7 +27,7 @@ def lib():
 
 def _build(case):
     from pyscenedetect_b200.compat import FlashFilter
-    from pyscenedetect_b200.detectors import (AdaptiveDetector, ContentDetector, HistogramDetector,
+    from pyscenedetect_b200.detectors import (AdaptiveDetector, ContentDetector, HashDetector, HistogramDetector,
                                               ThresholdDetector)
     kw = dict(case["kw"])
     if "weights" in kw:
@@ -37,7 +37,7 @@ def _build(case):
     if "method" in kw:
         kw["method"] = ThresholdDetector.Method[kw["method"]]
     cls = {"content": ContentDetector, "adaptive": AdaptiveDetector, "threshold": ThresholdDetector,
-           "histogram": HistogramDetector}[case["det"]]
+           "histogram": HistogramDetector, "hash": HashDetector}[case["det"]]
     return cls(**kw)
 
 
@@ -514,12 +514,13 @@ def test_device_cut_state_machines_match_golden(lib, name):
     weights = tuple(kw.get("weights", (1.0, 1.0, 1.0, 0.0)))
     if kw.get("luma_only"):
         weights = (0.0, 0.0, 1.0, 0.0)
-    feats = {"content": F_HSV, "adaptive": F_HSV, "threshold": F_BGRSUM, "histogram": F_YHIST}[det]
+    feats = {"content": F_HSV, "adaptive": F_HSV, "threshold": F_BGRSUM, "histogram": F_YHIST, "hash": 16}[det]
     if det in ("content", "adaptive") and weights[3] > 0.0:
         feats |= F_EDGES
     size = _scored_size(case) or (frames.shape[2], frames.shape[1])
     eng = Engine(frames.shape[2], frames.shape[1], feats, width=size[0], height=size[1], max_batch=64,
-                 edge_kernel_size=kw.get("kernel_size") or 0)
+                 edge_kernel_size=kw.get("kernel_size") or 0, hash_size=kw.get("size", 8),
+                 hash_lowpass=kw.get("lowpass", 2))
     eng.submit(frames)
     dc = DeviceCuts(eng)
     fps = case["fps"]
@@ -531,6 +532,8 @@ def test_device_cut_state_machines_match_golden(lib, name):
                            kw.get("min_content_val", 15.0), fps)
     elif det == "histogram":
         cuts = dc.histogram(kw.get("threshold", 0.20), kw.get("bins", 128), msl, fps)
+    elif det == "hash":
+        cuts = dc.hash(kw.get("threshold", 0.35), msl, fps)
     else:
         cuts = dc.threshold(kw.get("threshold", 12), msl, kw.get("fade_bias", 0.0), kw.get("add_final_scene", False),
                             kw.get("method") == "CEILING", fps)
@@ -551,12 +554,13 @@ def test_gathered_results_device_automata_match_golden(lib, name):
     det = _build(case)
     size = _scored_size(case) or (frames.shape[2], frames.shape[1])
     eng = Engine(frames.shape[2], frames.shape[1], det.required_features(), width=size[0], height=size[1],
-                 max_batch=64, edge_kernel_size=det.edge_kernel_size_arg())
+                 max_batch=64, edge_kernel_size=det.edge_kernel_size_arg(), **det.engine_kwargs())
     eng.submit(frames)
     sums = eng.read_sums()
     hist = eng.read_yhist() if det.required_features() & F_YHIST else None
+    hashes = eng.read_hash() if det.required_features() & 16 else None
     eng.close()
-    res = GatheredResults(sums, hist, size[0] * size[1])
+    res = GatheredResults(sums, hist, size[0] * size[1], hashes=hashes, **det.engine_kwargs())
     assert sorted(set(cuts_for_detector(DeviceCuts(res), det, case["fps"]))) == case["cuts"]
 
 

@@ -17,7 +17,8 @@ def build_ref(case, with_stats):
     if "method" in kw:
         kw["method"] = {"FLOOR": 0, "CEILING": 1}[kw["method"]]
     cls = {"content": R.RefContentDetector, "adaptive": R.RefAdaptiveDetector,
-           "threshold": R.RefThresholdDetector, "histogram": R.RefHistogramDetector}[det]
+           "threshold": R.RefThresholdDetector, "histogram": R.RefHistogramDetector,
+           "hash": R.RefHashDetector}[det]
     return cls(fps=case["fps"], with_stats=with_stats, **kw)
 
 

@@ -45,7 +45,7 @@ def _worker(rank, world, port, case_name, q):
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("case_name", ["content_default_nostats", "adaptive_w2", "hist_256",
-                                       "cfg1_threshold_360p", "content_edges_k3"])
+                                       "cfg1_threshold_360p", "content_edges_k3", "hash_default"])
 def test_sharded_equals_serial(case_name, world):
     from tests.golden_util import get_case
     if case_name == "cfg1_threshold_360p" and world == 3:
