@@ -62,17 +62,6 @@ __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, i
 // state.  No shared memory, no shuffles, no barrier; neighbouring threads re-read overlapping words from L1.
 constexpr int kBandRows = 32;
 
-// direction sector of a pixel (OpenCV's fixed-point tangent test), branch-free: 0 = compare left/right,
-// 1 = up/down, 2 = the (y-1,x-1)/(y+1,x+1) diagonal, 3 = the (y-1,x+1)/(y+1,x-1) diagonal
-__device__ __forceinline__ uint32_t canny_sector(int gx, int gy) {
-    const int ax = abs(gx);
-    const int ay = abs(gy) << 15;
-    const int tg22x = ax * 13573;
-    const int tg67x = tg22x + (ax << 16);
-    const uint32_t diag = ((gx ^ gy) < 0) ? 3u : 2u;
-    return (ay < tg22x) ? 0u : ((ay > tg67x) ? 1u : diag);
-}
-
 // sum of (unsigned byte of a) x (signed byte of b): the C++ __dp4a overloads are all-signed or all-unsigned
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
     int d;
@@ -132,34 +121,57 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
 
     int cA[10], cB[10], hA[10], hB[10];   // sums of the two most recent rows (roles alternate)
     int mU[10], mC[10], mD[10];           // magnitudes of rows y-1, y, y+1
-    uint32_t dirC = 0, dirD = 0;          // direction sectors of the 8 output columns (2 bits each), rows y, y+1
+    // direction sectors of the 8 output columns of rows y / y+1 as two 8-bit masks (OpenCV's fixed-point
+    // tangent test): (hi, lo) = 00 compare left/right, 01 up/down, 10 the (y-1,x-1)/(y+1,x+1) diagonal,
+    // 11 the (y-1,x+1)/(y+1,x-1) diagonal
+    uint32_t dloC = 0, dhiC = 0, dloD = 0, dhiD = 0;
     // Row `yy+1` arrives: gradient of row yy from rows yy-1 (`co`/`ho`, overwritten with row yy+1 on the way
-    // out), yy (`cm`) and yy+1.  Magnitudes go to `m`, sectors to `dir` (only if some pixel can be a candidate).
-    auto advance = [&](int yy, int (&co)[10], const int (&cm)[10], int (&ho)[10], int (&m)[10], uint32_t& dir) {
+    // out), yy (`cm`) and yy+1.  Magnitudes go to `m`, sectors to (dlo, dhi) if some pixel can be a candidate.
+    auto advance = [&](int yy, int (&co)[10], const int (&cm)[10], int (&ho)[10], int (&m)[10], uint32_t& dlo,
+                       uint32_t& dhi) {
         uint32_t w[4];
         load_window(yy + 1, w);
-        const bool row_in = yy >= 0 && yy < H;
         int gxs[8], gys[8];
         bool any = false;
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
             int hn, cn;
             col_sums(w, i, hn, cn);
-            const bool in = row_in && ((col_in >> i) & 1u);
-            const int gx = in ? co[i] + 2 * cm[i] + cn : 0;
-            const int gy = in ? hn - ho[i] : 0;
+            const int gx = co[i] + 2 * cm[i] + cn;
+            const int gy = hn - ho[i];
             co[i] = cn;
             ho[i] = hn;
             m[i] = abs(gx) + abs(gy);
-            if (i >= 1 && i <= 8) {
-                gxs[i - 1] = gx; gys[i - 1] = gy;
-                any |= m[i] > low;
-            }
+            if (i >= 1 && i <= 8) { gxs[i - 1] = gx; gys[i - 1] = gy; }
         }
-        dir = 0;
+        // gradients outside the image are zero (cv2 pads the magnitude buffer): whole rows above / below the
+        // image, and the columns left / right of it (only the first / last strip has any)
+        if (yy < 0 || yy >= H) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) m[i] = 0;
+        }
+        if (ALIGNED) {
+            if (sx == 0) m[0] = 0;
+            if (x0 + 8 >= W) m[9] = 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 10; ++i)
+                if (!((col_in >> i) & 1u)) m[i] = 0;
+        }
+#pragma unroll
+        for (int i = 1; i <= 8; ++i) any |= m[i] > low;
+        dlo = dhi = 0;
         if (any) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dir |= canny_sector(gxs[i], gys[i]) << (2 * i);
+            for (int i = 0; i < 8; ++i) {
+                const int ax = abs(gxs[i]), ay = abs(gys[i]);
+                const int t22 = ax * 13573 - (ay << 15);        // > 0  <=>  ay*2^15 < tg22 * ax
+                const int t67 = t22 + (ax << 16);               // < 0  <=>  ay*2^15 > tg67 * ax
+                const bool horiz = t22 > 0, vert = t67 < 0;
+                const bool diag = !horiz && !vert;
+                if (diag) dhi |= 1u << i;
+                if (vert || (diag && ((gxs[i] ^ gys[i]) < 0))) dlo |= 1u << i;
+            }
         }
     };
     // prologue: rows yb-2, yb-1 into (A, B); gradients of rows yb-1 and yb
@@ -171,35 +183,40 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
         load_window(yb - 1, w);
 #pragma unroll
         for (int i = 0; i < 10; ++i) col_sums(w, i, hB[i], cB[i]);
-        uint32_t unused;
-        advance(yb - 1, cA, cB, hA, mU, unused);   // A: yb-2 -> yb
-        advance(yb, cB, cA, hB, mC, dirC);         // B: yb-1 -> yb+1
+        uint32_t u0, u1;
+        advance(yb - 1, cA, cB, hA, mU, u0, u1);   // A: yb-2 -> yb
+        advance(yb, cB, cA, hB, mC, dloC, dhiC);   // B: yb-1 -> yb+1
     }
     // one output row y: on entry (co, ho) hold row y, (cm) row y+1
     auto row_step = [&](int y, int (&co)[10], const int (&cm)[10], int (&ho)[10]) {
-        advance(y + 1, co, cm, ho, mD, dirD);
+        advance(y + 1, co, cm, ho, mD, dloD, dhiD);
         uint32_t ebyte = 0, cbyte = 0;
         bool any = false;
 #pragma unroll
         for (int i = 1; i <= 8; ++i) any |= mC[i] > low;
         if (any) {
+            // the four non-maximum tests of every pixel as bit masks, then one mask expression picks by sector
+            uint32_t kH = 0, kV = 0, kD1 = 0, kD2 = 0, above = 0, strong = 0;
 #pragma unroll
-            for (int i = 1; i <= 8; ++i) {  // output column x0 + i - 1; every choice is a select, no branches
+            for (int i = 1; i <= 8; ++i) {
                 const int m = mC[i];
-                const uint32_t d = (dirC >> (2 * (i - 1))) & 3u;
-                const int n1 = d == 0u ? mC[i - 1] : d == 1u ? mU[i] : d == 2u ? mU[i - 1] : mU[i + 1];
-                const int n2 = d == 0u ? mC[i + 1] : d == 1u ? mD[i] : d == 2u ? mD[i + 1] : mD[i - 1];
-                // sectors 0 and 1 keep the pixel on "m >= second neighbour", the diagonals need "m >"
-                const bool keep = (m > low) && (m > n1) && (m + (d < 2u ? 1 : 0) > n2) && ((col_in >> i) & 1u);
-                cbyte |= keep ? (1u << (i - 1)) : 0u;
-                ebyte |= (keep && m > high) ? (1u << (i - 1)) : 0u;
+                const uint32_t bit = 1u << (i - 1);
+                if (m > mC[i - 1] && m >= mC[i + 1]) kH |= bit;
+                if (m > mU[i] && m >= mD[i]) kV |= bit;
+                if (m > mU[i - 1] && m > mD[i + 1]) kD1 |= bit;
+                if (m > mU[i + 1] && m > mD[i - 1]) kD2 |= bit;
+                if (m > low) above |= bit;
+                if (m > high) strong |= bit;
             }
+            const uint32_t keep = ((~dhiC & ~dloC & kH) | (~dhiC & dloC & kV) | (dhiC & ~dloC & kD1) | (dhiC & dloC & kD2)) & above;
+            cbyte = keep & 0xFFu;
+            ebyte = keep & strong & 0xFFu;
         }
         eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
         cout[(int64_t)y * row_bytes] = (uint8_t)cbyte;
 #pragma unroll
         for (int i = 0; i < 10; ++i) { mU[i] = mC[i]; mC[i] = mD[i]; }
-        dirC = dirD;
+        dloC = dloD; dhiC = dhiD;
     };
     // after the prologue: A holds row yb, B row yb+1
 #pragma unroll 1
@@ -239,91 +256,102 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t per_frame_tiles = (int64_t)tiles_x * tiles_y;
     const int64_t frame_words = (int64_t)H * Wq;
+    // a warp owns a contiguous run of tiles: their dirty bytes are read 32 at a time, one per lane
+    const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
+    const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles);
 
     for (int round = 0; round < 100000; ++round) {
         uint8_t* dcur = dirty + (int64_t)(round & 1) * n_tiles;
         uint8_t* dnext = dirty + (int64_t)((round + 1) & 1) * n_tiles;
         if (blockIdx.x == 0 && threadIdx.x == 0) flags[(round + 1) % 3] = 0;
         bool warp_changed = false;
-        for (int64_t t = warp0; t < n_tiles; t += n_warps) {
-            if (round > 0) {
-                if (dcur[t] == 0) continue;   // warp-uniform
-                __syncwarp();
-                if (lane == 0) dcur[t] = 0;
+        for (int64_t base = t_begin; base < t_end; base += 32) {
+            uint32_t todo;  // bit l: tile base + l needs a visit this round
+            {
+                const int64_t mine = base + lane;
+                bool need = mine < t_end;
+                if (need && round > 0) {
+                    need = dcur[mine] != 0;
+                    if (need) dcur[mine] = 0;
+                }
+                todo = __ballot_sync(0xFFFFFFFFu, need);
             }
-            const int64_t f = t / per_frame_tiles;
-            const int tt = (int)(t - f * per_frame_tiles);
-            const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-            const int y0 = ty * kHystTileH, wq0 = tx * 2;
-            const int y = y0 + lane;
-            uint32_t* E = edge_bits + f * frame_words;
-            const uint32_t* C = cand_bits + f * frame_words;
-            const bool row_in = y < H;
-            const bool has_w1 = wq0 + 1 < Wq;
-            const bool has_left = wq0 > 0, has_right = wq0 + 2 < Wq;
-            // candidate / edge words of this lane's row
-            unsigned long long c = 0, e = 0;
-            uint32_t lbit = 0, rbit = 0;   // E of the pixel left of column 0 / right of column 63, this row
-            auto load_row64 = [&](const uint32_t* plane, int yy) -> unsigned long long {
-                const uint32_t* p = plane + (int64_t)yy * Wq + wq0;
-                const unsigned long long lo = p[0];
-                const unsigned long long hi = has_w1 ? p[1] : 0u;
-                return lo | (hi << 32);
-            };
-            auto side_bits = [&](int yy, uint32_t& l, uint32_t& r) {
-                const uint32_t* p = E + (int64_t)yy * Wq + wq0;
-                l = has_left ? (p[-1] >> 31) : 0u;
-                r = has_right ? (p[2] & 1u) : 0u;
-            };
-            if (row_in) {
-                c = load_row64(C, y);
-                e = load_row64(E, y);
-                side_bits(y, lbit, rbit);
-            }
-            // weak pixels left in this tile?  (warp-uniform exit: nothing can change)
-            if (__ballot_sync(0xFFFFFFFFu, (c & ~e) != 0ull) == 0u) continue;
-            // ring rows above / below the tile (lane 0 / lane 31 supply them to the shuffles)
-            unsigned long long e_above = 0, e_below = 0;
-            uint32_t l_above = 0, r_above = 0, l_below = 0, r_below = 0;
-            if (lane == 0 && y0 > 0) { e_above = load_row64(E, y0 - 1); side_bits(y0 - 1, l_above, r_above); }
-            if (lane == 31 && y0 + kHystTileH < H) {
-                e_below = load_row64(E, y0 + kHystTileH);
-                side_bits(y0 + kHystTileH, l_below, r_below);
-            }
-            // the side columns do not change while the tile iterates: fold them into two seed bits per row
-            uint32_t lu = __shfl_up_sync(0xFFFFFFFFu, lbit, 1), ld = __shfl_down_sync(0xFFFFFFFFu, lbit, 1);
-            uint32_t ru = __shfl_up_sync(0xFFFFFFFFu, rbit, 1), rd = __shfl_down_sync(0xFFFFFFFFu, rbit, 1);
-            if (lane == 0) { lu = l_above; ru = r_above; }
-            if (lane == 31) { ld = l_below; rd = r_below; }
-            unsigned long long side_seed = 0;
-            if (lu | lbit | ld) side_seed |= 1ull;
-            if (ru | rbit | rd) side_seed |= 1ull << 63;
-            const unsigned long long e_in = e;
-            while (true) {
-                unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, e, 1), d = __shfl_down_sync(0xFFFFFFFFu, e, 1);
-                if (lane == 0) u = e_above;
-                if (lane == 31) d = e_below;
-                const unsigned long long v = u | d;
-                const unsigned long long nb = v | (v << 1) | (v >> 1) | side_seed;
-                const unsigned long long t2 = (nb & c) | e;
-                const unsigned long long e2 = run_fill(t2, c);
-                const bool ch = e2 != e;
-                e = e2;
-                if (__ballot_sync(0xFFFFFFFFu, ch) == 0u) break;
-            }
-            const bool changed = e != e_in;
-            if (changed && row_in) {
-                uint32_t* p = E + (int64_t)y * Wq + wq0;
-                if ((uint32_t)e != (uint32_t)e_in) p[0] = (uint32_t)e;
-                if (has_w1 && (uint32_t)(e >> 32) != (uint32_t)(e_in >> 32)) p[1] = (uint32_t)(e >> 32);
-            }
-            if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
-                warp_changed = true;
-                // the ring of the 8 neighbours may have changed: they look again next round
-                if (lane < 9 && lane != 4) {
-                    const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
-                    if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x)
-                        dnext[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
+            while (todo) {
+                const int64_t t = base + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t f = t / per_frame_tiles;
+                const int tt = (int)(t - f * per_frame_tiles);
+                const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+                const int y0 = ty * kHystTileH, wq0 = tx * 2;
+                const int y = y0 + lane;
+                uint32_t* E = edge_bits + f * frame_words;
+                const uint32_t* C = cand_bits + f * frame_words;
+                const bool row_in = y < H;
+                const bool has_w1 = wq0 + 1 < Wq;
+                const bool has_left = wq0 > 0, has_right = wq0 + 2 < Wq;
+                // every load of the tile and of its ring is issued before the first use
+                uint32_t c_lo = 0, c_hi = 0, e_lo = 0, e_hi = 0, e_l = 0, e_r = 0;
+                if (row_in) {
+                    const uint32_t* pc = C + (int64_t)y * Wq + wq0;
+                    const uint32_t* pe = E + (int64_t)y * Wq + wq0;
+                    c_lo = pc[0];
+                    e_lo = pe[0];
+                    if (has_w1) { c_hi = pc[1]; e_hi = pe[1]; }
+                    if (has_left) e_l = pe[-1];
+                    if (has_right) e_r = pe[2];
+                }
+                // ring rows above / below the tile: lane 0 / lane 31 fetch them
+                const int ring_y = (lane == 0) ? y0 - 1 : y0 + kHystTileH;
+                const bool ring_in = (lane == 0 && y0 > 0) || (lane == 31 && y0 + kHystTileH < H);
+                uint32_t g_lo = 0, g_hi = 0, g_l = 0, g_r = 0;
+                if (ring_in) {
+                    const uint32_t* pe = E + (int64_t)ring_y * Wq + wq0;
+                    g_lo = pe[0];
+                    if (has_w1) g_hi = pe[1];
+                    if (has_left) g_l = pe[-1];
+                    if (has_right) g_r = pe[2];
+                }
+                const unsigned long long c = (unsigned long long)c_lo | ((unsigned long long)c_hi << 32);
+                unsigned long long e = (unsigned long long)e_lo | ((unsigned long long)e_hi << 32);
+                // weak pixels left in this tile?  (warp-uniform exit: nothing can change)
+                if (__ballot_sync(0xFFFFFFFFu, (c & ~e) != 0ull) == 0u) continue;
+                const uint32_t lbit = e_l >> 31, rbit = e_r & 1u;  // E left of column 0 / right of column 63, this row
+                const unsigned long long e_ring = (unsigned long long)g_lo | ((unsigned long long)g_hi << 32);
+                // the side columns do not change while the tile iterates: fold them into two seed bits per row
+                uint32_t lu = __shfl_up_sync(0xFFFFFFFFu, lbit, 1), ld = __shfl_down_sync(0xFFFFFFFFu, lbit, 1);
+                uint32_t ru = __shfl_up_sync(0xFFFFFFFFu, rbit, 1), rd = __shfl_down_sync(0xFFFFFFFFu, rbit, 1);
+                if (lane == 0) { lu = g_l >> 31; ru = g_r & 1u; }
+                if (lane == 31) { ld = g_l >> 31; rd = g_r & 1u; }
+                unsigned long long side_seed = 0;
+                if (lu | lbit | ld) side_seed |= 1ull;
+                if (ru | rbit | rd) side_seed |= 1ull << 63;
+                const unsigned long long e_in = e;
+                while (true) {
+                    unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, e, 1), d = __shfl_down_sync(0xFFFFFFFFu, e, 1);
+                    if (lane == 0) u = e_ring;
+                    if (lane == 31) d = e_ring;
+                    const unsigned long long v = u | d;
+                    const unsigned long long nb = v | (v << 1) | (v >> 1) | side_seed;
+                    const unsigned long long t2 = (nb & c) | e;
+                    const unsigned long long e2 = run_fill(t2, c);
+                    const bool ch = e2 != e;
+                    e = e2;
+                    if (__ballot_sync(0xFFFFFFFFu, ch) == 0u) break;
+                }
+                const bool changed = e != e_in;
+                if (changed && row_in) {
+                    uint32_t* p = E + (int64_t)y * Wq + wq0;
+                    if ((uint32_t)e != (uint32_t)e_in) p[0] = (uint32_t)e;
+                    if (has_w1 && (uint32_t)(e >> 32) != (uint32_t)(e_in >> 32)) p[1] = (uint32_t)(e >> 32);
+                }
+                if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
+                    warp_changed = true;
+                    // the ring of the 8 neighbours may have changed: they look again next round
+                    if (lane < 9 && lane != 4) {
+                        const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
+                        if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x)
+                            dnext[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
+                    }
                 }
             }
         }
@@ -450,7 +478,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
             PSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psd_hyst_bits_kernel, 256, 0));
             PSD_REQUIRE(per_sm > 0, "psd_hyst_bits_kernel does not fit on an SM");
-            grid_cap = sms * (per_sm < 4 ? per_sm : 4);
+            grid_cap = sms * per_sm;
         }
         const int64_t want = (n_tiles + 7) / 8;  // 8 warps per CTA, at least one tile per warp
         const int grid = (int)(want < grid_cap ? (want > 0 ? want : 1) : grid_cap);

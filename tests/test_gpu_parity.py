@@ -340,6 +340,39 @@ def test_histogram_path_matches_oracle_at_4k(lib):
         prev = hist
 
 
+@pytest.mark.parametrize("shape,size,lowpass", [((160, 90), 8, 2), ((256, 144), 8, 2), ((1920, 1080), 8, 2),
+                                                ((3840, 2160), 8, 2), ((131, 97), 4, 2), ((640, 360), 16, 4),
+                                                ((32, 32), 8, 2), ((64, 64), 16, 4), ((1280, 720), 12, 3)])
+def test_frame_hashes_match_cv2(lib, shape, size, lowpass):
+    """hash_detector.py:124-158: every hash bit of every frame vs the reference's own cv2 call sequence
+    (non-integer area scales, the integer-scale path incl. 2x2, mixed 1920x1080, no resize at all)."""
+    from pyscenedetect_b200.engine import F_HASH, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    w, h = shape
+    n = 6 if w * h > 1000000 else 24
+    frames = render_frames(ScenePlan(n, seed=w + size, min_len=2, max_len=5).params, w, h)
+    rng = np.random.default_rng(w)
+    extra = np.stack([np.zeros((h, w, 3), np.uint8), np.full((h, w, 3), 255, np.uint8),
+                      rng.integers(0, 256, (h, w, 3), dtype=np.uint8)])
+    frames = np.concatenate([frames, extra])
+    eng = Engine(w, h, F_HASH, max_batch=8, hash_size=size, hash_lowpass=lowpass)
+    eng.submit(frames)
+    got = eng.read_hash()
+    dist = eng.scan_hash_dist()
+    eng.close()
+    m = size * size
+    prev = None
+    for i, f in enumerate(frames):
+        want = R.hash_frame(f, size, lowpass).ravel()
+        bits = np.array([(int(got[i, k >> 6]) >> (k & 63)) & 1 for k in range(m)], dtype=bool)
+        assert np.array_equal(bits, want), (i, int((bits != want).sum()))
+        if prev is None:
+            assert np.isnan(dist[i])
+        else:
+            assert dist[i] == np.count_nonzero(want != prev) / float(m)
+        prev = want
+
+
 def test_errors_are_loud(lib):
     from pyscenedetect_b200 import FrameTimecode
     from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector
