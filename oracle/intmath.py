@@ -301,17 +301,55 @@ def resize_area(gray: np.ndarray, n: int) -> np.ndarray:
     return out
 
 
+def dct_fold_1d(v, size: int, costab: np.ndarray, n: int) -> list[float]:
+    """Unnormalised DCT-II coefficients u < size of `v`, computed as fast DCTs do (twin of
+    csrc/hash_kernels.cu:fold_coef): fold the vector (a[i] + a[len-1-i]) while its length is even; an even
+    frequency is the half frequency of the folded vector, an odd one a sum over differences a[i] - a[len-1-i],
+    accumulated left to right.  Constant / mirror-symmetric inputs give exact zeros."""
+    levels = [[float(t) for t in v]]
+    while len(levels[-1]) % 2 == 0 and len(levels[-1]) > 1 and len(levels) < 8:
+        a = levels[-1]
+        h = len(a) // 2
+        levels.append([a[i] + a[len(a) - 1 - i] for i in range(h)])
+    out = []
+    for u in range(size):
+        k = 0
+        if u == 0:
+            k = len(levels) - 1
+        else:
+            while k + 1 < len(levels) and u % (2 << k) == 0:
+                k += 1
+        a = levels[k]
+        nk = len(a)
+        acc = 0.0
+        if nk % 2 == 0 and (u >> k) & 1:
+            for i in range(nk // 2):
+                acc = acc + (a[i] - a[nk - 1 - i]) * float(costab[((2 * i + 1) * u) % (4 * n)])
+        else:
+            for i in range(nk):
+                acc = acc + a[i] * float(costab[((2 * i + 1) * u) % (4 * n)])
+        out.append(acc)
+    return out
+
+
 def phash_bits(bgr: np.ndarray, hash_size: int, factor: int) -> np.ndarray:
-    """hash_frame with the integer stages exact and the DCT in float64 (cv2.dct is float32 through IPP: a bit
-    can differ only where a coefficient sits within rounding distance of the median)."""
+    """hash_frame with the integer stages exact and the DCT in float64 with the folding structure of a fast DCT
+    (cv2.dct is float32 through IPP: a bit can differ only where a coefficient sits within rounding distance of the
+    median - in practice where the exact coefficient is 0: solid-colour frames and 1-D gradients; with the folding,
+    solid frames come out as cv2 gives them for power-of-two hash images)."""
+    import math
     n = hash_size * factor
     r = resize_area(bgr_to_gray(bgr), n)
     mx = int(r.max()) or 1
     x = (r.astype(np.float32) / np.float32(mx)).astype(np.float64)
-    k = np.arange(n)
-    C = np.cos(np.pi * (2 * k[None, :] + 1) * k[:, None] / (2 * n)) * np.sqrt(2.0 / n)
-    C[0, :] = np.sqrt(1.0 / n)
-    low = (C @ x @ C.T)[:hash_size, :hash_size].astype(np.float32)
+    costab = np.cos(np.pi * np.arange(4 * n) / (2.0 * n))
+    t = [dct_fold_1d(x[:, j], hash_size, costab, n) for j in range(n)]          # t[j][u]: vertical transform of column j
+    s0, s1 = math.sqrt(1.0 / n), math.sqrt(2.0 / n)
+    low = np.zeros((hash_size, hash_size), np.float32)
+    for u in range(hash_size):
+        row = dct_fold_1d([t[j][u] for j in range(n)], hash_size, costab, n)
+        for v in range(hash_size):
+            low[u, v] = np.float32((row[v] * (s1 if u else s0)) * (s1 if v else s0))
     flat = np.sort(low.ravel())
     m = flat.size
     med = flat[m // 2] if m % 2 else np.float32(np.float32(flat[m // 2 - 1] + flat[m // 2]) * np.float32(0.5))

@@ -48,6 +48,38 @@ __global__ void __launch_bounds__(256) psd_hash_rows_kernel(const uint8_t* __res
     }
 }
 
+// 1-D DCT-II (unnormalised) coefficient u of a vector, computed the way fast DCTs do: the vector is folded
+// (s[i] = a[i] + a[len-1-i]) as long as its length is even; an even frequency is the half frequency of the folded
+// vector, an odd frequency is a sum over DIFFERENCES a[i] - a[len-1-i].  Constant and mirror-symmetric inputs
+// therefore give exact zeros where the exact transform is zero (a plain sum of products leaves rounding noise of
+// random sign, and the hash is `coefficient > median`).  `lev` holds the folded levels back to back
+// (level k at lev + off[k], length len[k]; level 0 is the vector itself).  oracle/intmath.py:dct_fold_1d is the twin.
+struct FoldPlan {
+    int levels;        // number of levels including level 0
+    int len[8], off[8];
+};
+
+__device__ __forceinline__ double fold_coef(const double* v0, int stride0, const double* lev, int lstride,
+                                            const FoldPlan& fp, int n, int u, const double* costab) {
+    int k = 0;
+    if (u == 0) k = fp.levels - 1;
+    else while (k + 1 < fp.levels && (u & ((2 << k) - 1)) == 0) ++k;
+    const double* a = (k == 0) ? v0 : lev + (int64_t)fp.off[k] * lstride;
+    const int st = (k == 0) ? stride0 : lstride;
+    const int nk = fp.len[k];
+    double acc = 0.0;
+    if ((nk & 1) == 0 && ((u >> k) & 1)) {
+        for (int i = 0; i < nk / 2; ++i) {
+            const double d = __dsub_rn(a[(int64_t)i * st], a[(int64_t)(nk - 1 - i) * st]);
+            acc = __dadd_rn(acc, __dmul_rn(d, costab[((2 * i + 1) * u) % (4 * n)]));
+        }
+    } else {
+        for (int i = 0; i < nk; ++i)
+            acc = __dadd_rn(acc, __dmul_rn(a[(int64_t)i * st], costab[((2 * i + 1) * u) % (4 * n)]));
+    }
+    return acc;
+}
+
 // one CTA per frame: vertical pass, normalisation, DCT low band, median, bits
 constexpr int kHashMaxN = 64, kHashMaxSize = 16;
 __global__ void __launch_bounds__(256) psd_hash_finish_kernel(const float* __restrict__ rowbuf, int H, int n, int size,
@@ -55,13 +87,18 @@ __global__ void __launch_bounds__(256) psd_hash_finish_kernel(const float* __res
                                                               const int32_t* __restrict__ ystart,
                                                               const int32_t* __restrict__ ysi,
                                                               const float* __restrict__ ybeta,
-                                                              const double* __restrict__ cosn /* [size][n] */,
+                                                              const double* __restrict__ costab /* [4n] cos(pi k / 2n) */,
+                                                              FoldPlan fp,
                                                               uint64_t* __restrict__ hashes /* [frames][PSD_HASH_WORDS] */) {
-    __shared__ float x[kHashMaxN * kHashMaxN];
-    __shared__ double t[kHashMaxSize * kHashMaxN];
+    extern __shared__ __align__(16) double dsm[];
+    double* x = dsm;                    // [n][n] normalised image (row i, column j)
+    double* lev = x + n * n;            // [n][n]: folded levels of every column j (element e of column j at lev[e*n + j])
+    double* t = lev + n * n;            // [size][n]: vertical transform, t[u][j]
+    double* lev2 = t + size * n;        // [n][size]: folded levels of every t[u][.] (element e of row u at lev2[e*size + u])
     __shared__ float low[kHashMaxSize * kHashMaxSize];
     __shared__ uint32_t mx;
     __shared__ float med;
+    __shared__ float mid[2];
     __shared__ unsigned long long bits[PSD_HASH_WORDS];
     const int tid = threadIdx.x;
     const int64_t f = blockIdx.x;
@@ -87,32 +124,51 @@ __global__ void __launch_bounds__(256) psd_hash_finish_kernel(const float* __res
             }
             v = (uint32_t)min(max(__float2int_rn(sum), 0), 255);
         }
-        x[c] = (float)v;
+        x[c] = (double)v;
         my_max = max(my_max, v);
     }
     atomicMax(&mx, my_max);
     __syncthreads();
     const float denom = (float)(mx ? mx : 1u);
-    for (int c = tid; c < n * n; c += 256) x[c] = __fdiv_rn(x[c], denom);
+    for (int c = tid; c < n * n; c += 256) x[c] = (double)__fdiv_rn((float)x[c], denom);
     __syncthreads();
-    // D = C x C^T restricted to the low band: t[u][j] = sum_i C[u][i] x[i][j], D[u][v] = sum_j t[u][j] C[v][j]
+    // folded levels of every column (level k from level k-1)
+    for (int k = 1; k < fp.levels; ++k) {
+        const int len = fp.len[k], plen = fp.len[k - 1];
+        for (int c = tid; c < len * n; c += 256) {
+            const int e = c / n, j = c - e * n;
+            const double* prev = (k == 1) ? x : lev + (int64_t)fp.off[k - 1] * n;
+            lev[(int64_t)(fp.off[k] + e) * n + j] = __dadd_rn(prev[(int64_t)e * n + j], prev[(int64_t)(plen - 1 - e) * n + j]);
+        }
+        __syncthreads();
+    }
+    // vertical transform: t[u][j] = sum_i x[i][j] cos(pi (2i+1) u / 2n), u < size
     for (int c = tid; c < size * n; c += 256) {
         const int u = c / n, j = c - u * n;
-        double acc = 0.0;
-        for (int i = 0; i < n; ++i) acc = fma(cosn[u * n + i], (double)x[i * n + j], acc);
-        t[c] = acc;
+        t[c] = fold_coef(x + j, n, lev + j, n, fp, n, u, costab);
     }
     __syncthreads();
+    for (int k = 1; k < fp.levels; ++k) {
+        const int len = fp.len[k], plen = fp.len[k - 1];
+        for (int c = tid; c < len * size; c += 256) {
+            const int e = c / size, u = c - e * size;
+            double pa, pb;
+            if (k == 1) { pa = t[u * n + e]; pb = t[u * n + plen - 1 - e]; }
+            else { pa = lev2[(int64_t)(fp.off[k - 1] + e) * size + u]; pb = lev2[(int64_t)(fp.off[k - 1] + plen - 1 - e) * size + u]; }
+            lev2[(int64_t)(fp.off[k] + e) * size + u] = __dadd_rn(pa, pb);
+        }
+        __syncthreads();
+    }
+    // horizontal transform + orthonormal scale: D[u][v] = s(u) s(v) sum_j t[u][j] cos(pi (2j+1) v / 2n)
     const int m = size * size;
+    const double s0 = sqrt(1.0 / n), s1 = sqrt(2.0 / n);
     for (int c = tid; c < m; c += 256) {
         const int u = c / size, v = c - u * size;
-        double acc = 0.0;
-        for (int j = 0; j < n; ++j) acc = fma(t[u * n + j], cosn[v * n + j], acc);
-        low[c] = (float)acc;
+        const double acc = fold_coef(t + u * n, 1, lev2 + u, size, fp, n, v, costab);
+        low[c] = (float)__dmul_rn(__dmul_rn(acc, u ? s1 : s0), v ? s1 : s0);
     }
     __syncthreads();
     // numpy.median: rank every element (ties broken by index), pick the middle one / the float32 mean of the two
-    __shared__ float mid[2];
     for (int c = tid; c < m; c += 256) {
         const float a = low[c];
         int rank = 0;
@@ -186,12 +242,19 @@ int hash_plan_create(HashPlan* p, int W, int H, int size, int lowpass, int max_b
     rc = upload(st, &p->ystart); if (rc) return rc;
     rc = upload(si, &p->ysi); if (rc) return rc;
     rc = upload(al, &p->ybeta); if (rc) return rc;
-    std::vector<double> c((size_t)size * n);
-    const double pi = 3.14159265358979323846;
-    for (int u = 0; u < size; ++u)
-        for (int i = 0; i < n; ++i)
-            c[(size_t)u * n + i] = (u == 0) ? sqrt(1.0 / n) : cos(pi * (2 * i + 1) * u / (2.0 * n)) * sqrt(2.0 / n);
+    std::vector<double> c((size_t)4 * n);
+    const double pi = 3.141592653589793;
+    for (int k = 0; k < 4 * n; ++k) c[k] = cos(pi * k / (2.0 * n));   // numpy: cos(pi * k / (2 n)), same expression
     rc = upload(c, &p->cosn); if (rc) return rc;
+    // folded levels: level k+1 exists while level k has even length
+    p->levels = 1; p->len[0] = n; p->off[0] = 0;
+    int off = 0;
+    while ((p->len[p->levels - 1] & 1) == 0 && p->len[p->levels - 1] > 1 && p->levels < 8) {
+        p->len[p->levels] = p->len[p->levels - 1] / 2;
+        p->off[p->levels] = off;
+        off += p->len[p->levels];
+        p->levels += 1;
+    }
     PSD_CUDA(cudaMalloc(&p->rowbuf, (size_t)max_batch * H * n * sizeof(float)));
     return PSD_OK;
 }
@@ -208,8 +271,13 @@ int launch_hash(const HashPlan& p, const uint8_t* frames, int64_t frame_stride, 
     psd_hash_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(frames, frame_stride, W, H, p.n, p.fast,
                                                                              p.xstart, p.xsi, p.xalpha, p.rowbuf, total);
     PSD_CHECK_LAUNCH();
-    psd_hash_finish_kernel<<<(unsigned)n_frames, 256, 0, stream>>>(p.rowbuf, H, p.n, p.size, p.fast, p.area_w, p.area_h,
-                                                                  p.ystart, p.ysi, p.ybeta, p.cosn, hashes);
+    FoldPlan fp{};
+    fp.levels = p.levels;
+    for (int k = 0; k < 8; ++k) { fp.len[k] = p.len[k]; fp.off[k] = p.off[k]; }
+    const size_t smem = ((size_t)2 * p.n * p.n + (size_t)p.size * p.n + (size_t)p.n * p.size) * sizeof(double);
+    PSD_CUDA(cudaFuncSetAttribute(psd_hash_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    psd_hash_finish_kernel<<<(unsigned)n_frames, 256, smem, stream>>>(p.rowbuf, H, p.n, p.size, p.fast, p.area_w, p.area_h,
+                                                                     p.ystart, p.ysi, p.ybeta, p.cosn, fp, hashes);
     PSD_CHECK_LAUNCH();
     count_launch(2);
     return PSD_OK;

@@ -103,7 +103,8 @@ struct HashPlan {        // per-engine tables for one (frame size, hash size, lo
     int area_w = 0, area_h = 0;
     int32_t *xstart = nullptr, *xsi = nullptr, *ystart = nullptr, *ysi = nullptr;
     float *xalpha = nullptr, *ybeta = nullptr;
-    double* cosn = nullptr;   // [size][n] DCT-II basis rows
+    double* cosn = nullptr;   // [4n] cos(pi k / 2n)
+    int levels = 1, len[8] = {0}, off[8] = {0};  // folded levels of a length-n vector (hash_kernels.cu:FoldPlan)
     float* rowbuf = nullptr;  // [max_batch][H][n] horizontal pass
 };
 int hash_plan_create(HashPlan* p, int W, int H, int size, int lowpass, int max_batch);

@@ -19,6 +19,6 @@ for cfg in "$@"; do
   tag=${cfg%%:*}
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o build/alt_$tag.so build/engine.o \
        build_alt/score_kernel_$tag.o build/edge_kernels.o build/resize_kernel.o build/scan_kernels.o \
-       build/cut_kernels.o build/synth_kernel.o
+       build/cut_kernels.o build/hash_kernels.o build/synth_kernel.o
   echo "built build/alt_$tag.so: $(python ../../tools/sass_loop_stats.py build/alt_$tag.so | head -1 | sed 's/.*consumer loop//')"
 done
