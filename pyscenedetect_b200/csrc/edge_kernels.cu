@@ -60,7 +60,7 @@ __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, i
 // arithmetic on those sums:  gx = c(y-1) + 2 c(y) + c(y+1),  gy = h(y+1) - h(y-1); two rows of sums,
 // three rows of magnitudes and the 2-bit direction sector of the pixels above the low threshold are all the
 // state.  No shared memory, no shuffles, no barrier; neighbouring threads re-read overlapping words from L1.
-constexpr int kBandRows = 32;
+constexpr int kBandRows = 32;   // == kHystTileH: a band of the classify kernel is one tile row of the hysteresis
 
 // sum of (unsigned byte of a) x (signed byte of b): the C++ __dp4a overloads are all-signed or all-unsigned
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
@@ -72,7 +72,8 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
-    uint32_t* __restrict__ cand_bits, int W, int H, int Wq, int strips, int bands, int64_t n_threads) {
+    uint32_t* __restrict__ cand_bits, uint8_t* __restrict__ tile_dirty, int W, int H, int Wq, int strips,
+    int bands, int64_t n_threads) {
     const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (gid >= n_threads) return;
     const int sx = (int)(gid % strips);
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
         c = dp4a_u8_s8(t, 0x000100FFu);   // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
     };
 
+    uint32_t weak_seen = 0;               // some candidate of this band is not strong: its tile needs hysteresis
     int cA[10], cB[10], hA[10], hB[10];   // sums of the two most recent rows (roles alternate)
     int mU[10], mC[10], mD[10];           // magnitudes of rows y-1, y, y+1
     // direction sectors of the 8 output columns of rows y / y+1 as two 8-bit masks (OpenCV's fixed-point
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
         }
         eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
         cout[(int64_t)y * row_bytes] = (uint8_t)cbyte;
+        weak_seen |= cbyte & ~ebyte;
 #pragma unroll
         for (int i = 0; i < 10; ++i) { mU[i] = mC[i]; mC[i] = mD[i]; }
         dloC = dloD; dhiC = dhiD;
@@ -223,6 +226,11 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
     for (int y = yb; y < ye; y += 2) {
         row_step(y, cA, cB, hA);
         if (y + 1 < ye) row_step(y + 1, cB, cA, hB);
+    }
+    // a band is exactly one hysteresis tile row high (kBandRows == kHystTileH) and 8 of its 64 columns wide
+    if (weak_seen) {
+        const int tiles_x = (Wq + 1) / 2;
+        tile_dirty[(f * bands + by) * (int64_t)tiles_x + (x0 >> 6)] = 1;
     }
 }
 
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
 // the one-pixel ring around it from the neighbouring tiles' E words.  Tiles whose ring may have changed are
 // revisited in the next round; rounds are separated by a grid-wide barrier of a cooperative launch, so a
 // batch costs ONE launch however long the weak chains are (a chain advances at least one tile per round).
-constexpr int kHystTileW = 64, kHystTileH = 32;
+constexpr int kHystTileH = 32;  // tiles are 64 columns (two words) x 32 rows
 
 __device__ __forceinline__ unsigned long long run_fill(unsigned long long t, unsigned long long c) {
     // t subset of c: every maximal run of 1-bits of c that contains a bit of t, completely
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
             {
                 const int64_t mine = base + lane;
                 bool need = mine < t_end;
-                if (need && round > 0) {
+                if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
                     need = dcur[mine] != 0;
                     if (need) dcur[mine] = 0;
                 }
@@ -457,19 +465,20 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
             PSD_CUDA(cudaMemsetAsync(b.bits_in, 0, (size_t)per_frame * 4 * n, stream));
             PSD_CUDA(cudaMemsetAsync(b.cand, 0, (size_t)per_frame * 4 * n, stream));
         }
+        const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
+        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles0, stream));
         if ((W & 7) == 0)
             psd_canny_classify_bits_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
-                                                                             W, H, Wq, strips, bands, n_threads);
+                                                                             b.dirty, W, H, Wq, strips, bands, n_threads);
         else
             psd_canny_classify_bits_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
-                                                                              W, H, Wq, strips, bands, n_threads);
+                                                                              b.dirty, W, H, Wq, strips, bands, n_threads);
         PSD_CHECK_LAUNCH();
     }
     // hysteresis: one cooperative launch (grid = what is co-resident on the device)
     {
         int tiles_x = (Wq + 1) / 2, tiles_y = (H + kHystTileH - 1) / kHystTileH;
         int64_t n_tiles = (int64_t)tiles_x * tiles_y * n;
-        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles, stream));
         PSD_CUDA(cudaMemsetAsync(b.hyst_flags, 0, 3 * sizeof(int32_t), stream));
         static int grid_cap = 0;
         if (grid_cap == 0) {

