@@ -18,27 +18,54 @@
 // batch: profiles/r01w_launches_content_edges_summary.txt).
 #include <cooperative_groups.h>
 
+#include "canny_pairs.cuh"
 #include "psd_common.cuh"
 
 namespace cg = cooperative_groups;
 
+#ifndef PSD_HYST_STATS
+#define PSD_HYST_STATS 0
+#endif
+#ifndef PSD_CLASSIFY_PAIRS
+#define PSD_CLASSIFY_PAIRS 1
+#endif
+
 namespace psd {
 
 // ---- 1. per-frame Canny thresholds from the V histogram ----
+// one warp per frame: lane l owns bins 8l .. 8l+7; an inclusive warp scan of the lane totals locates the two
+// order statistics
 __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, int n, int64_t n_pixels,
                                            int32_t* __restrict__ thr) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (f >= n) return;
-    const uint32_t* h = vhist + (int64_t)f * 256;
+    const uint4* h4 = reinterpret_cast<const uint4*>(vhist + (int64_t)f * 256) + 2 * lane;
+    const uint4 a = h4[0], b = h4[1];
+    const uint32_t bins[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t own = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) own += bins[i];
+    uint32_t incl = own;   // a frame has fewer than 2^32 pixels
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += up;
+    }
     // numpy.median: mean of the order statistics (n-1)//2 and n//2 (0-based)
     const int64_t r_lo = (n_pixels - 1) / 2 + 1, r_hi = n_pixels / 2 + 1;
-    int lo = -1, hi = -1;
-    int64_t cum = 0;
-    for (int i = 0; i < 256; ++i) {
-        cum += h[i];
-        if (lo < 0 && cum >= r_lo) lo = i;
-        if (hi < 0 && cum >= r_hi) hi = i;
+    int64_t cum = (int64_t)incl - own;
+    int lo_l = -1, hi_l = -1;   // first bin of this lane whose cumulative count reaches the rank
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t before = cum;
+        cum += bins[i];
+        if (before < r_lo && cum >= r_lo) lo_l = 8 * lane + i;
+        if (before < r_hi && cum >= r_hi) hi_l = 8 * lane + i;
     }
+    // exactly one lane sees each crossing
+    const int lo = __reduce_max_sync(0xFFFFFFFFu, lo_l), hi = __reduce_max_sync(0xFFFFFFFFu, hi_l);
+    if (lane != 0) return;
     const double median = __ddiv_rn((double)(lo + hi), 2.0);
     const double sigma = __ddiv_rn(1.0, 3.0);
     const double lo_d = __dmul_rn(__dsub_rn(1.0, sigma), median);
@@ -234,6 +261,161 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
     }
 }
 
+// ---- 2b. the same stage on pixel pairs (canny_pairs.cuh): two 16-bit lanes per register ----
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
+    const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
+    uint32_t* __restrict__ cand_bits, uint8_t* __restrict__ tile_dirty, int W, int H, int Wq, int strips,
+    int bands, int64_t n_threads) {
+    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gid >= n_threads) return;
+    const int sx = (int)(gid % strips);
+    const int by = (int)((gid / strips) % bands);
+    const int64_t f = gid / ((int64_t)strips * bands);
+    const int64_t P = (int64_t)W * H;
+    const uint8_t* src = vplane + f * P;
+    uint8_t* eout = reinterpret_cast<uint8_t*>(edge_bits + f * (int64_t)H * Wq) + sx;
+    uint8_t* cout = reinterpret_cast<uint8_t*>(cand_bits + f * (int64_t)H * Wq) + sx;
+    const uint32_t low1 = cp::scaled2(thr[2 * f] + 1), high1 = cp::scaled2(thr[2 * f + 1] + 1);
+    const int x0 = sx * 8;
+    const int yb = by * kBandRows, ye = min(yb + kBandRows, H);
+    const int row_bytes = Wq * 4;
+    // lanes of the pairs that lie inside the image (gradients outside are zero: cv2 pads the magnitude buffer)
+    uint32_t inO[4], inL[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        inO[k] = (x0 + 2 * k < W ? 0x0000FFFFu : 0u) | (x0 + 2 * k + 1 < W ? 0xFFFF0000u : 0u);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        inL[k] = ((x0 + 2 * k - 1 >= 0 && x0 + 2 * k - 1 < W) ? 0x0000FFFFu : 0u) | (x0 + 2 * k < W ? 0xFFFF0000u : 0u);
+
+    // the 16 bytes x0-4 .. x0+11 of row y (BORDER_REPLICATE in both directions)
+    auto load_window = [&](int y, uint32_t (&w)[4]) {
+        const int yc = min(max(y, 0), H - 1);
+        const uint8_t* row = src + (int64_t)yc * W;
+        if (ALIGNED) {  // W % 8 == 0: every strip is whole, words are 4-byte aligned
+            const uint2 mid = *reinterpret_cast<const uint2*>(row + x0);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(row) + 2 * sx;
+            w[1] = mid.x;
+            w[2] = mid.y;
+            w[0] = (sx > 0) ? rw[-1] : __byte_perm(w[1], 0, 0x0000);        // replicate column 0
+            w[3] = (x0 + 8 < W) ? rw[2] : __byte_perm(w[2], 0, 0x3333);     // replicate column W-1
+        } else {
+            w[0] = w[1] = w[2] = w[3] = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int x = min(max(x0 - 4 + k, 0), W - 1);
+                w[k >> 2] |= (uint32_t)row[x] << (8 * (k & 3));
+            }
+        }
+    };
+    // Row yy+1 arrives: magnitudes (and, if asked, sectors) of row yy from the sums of rows yy-1 (`so`,
+    // replaced by row yy+1 on the way out), yy (`sm`) and yy+1.
+    auto advance = [&](int yy, cp::Sums& so, const cp::Sums& sm, cp::Mags& r, bool want_sectors) {
+        uint32_t w[4];
+        load_window(yy + 1, w);
+        cp::Sums sn;
+        cp::row_sums(w, sn);
+        uint32_t gxO[4], gyO[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gxO[k] = cp::hadd(cp::hfma(sm.cO[k], cp::kTwo, so.cO[k]), sn.cO[k]);
+            gyO[k] = cp::hsub(sn.hO[k], so.hO[k]);
+            r.mO[k] = cp::habs_sum(gxO[k], gyO[k]);
+            if (!ALIGNED) r.mO[k] &= inO[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t gx = cp::hadd(cp::hfma(sm.cL[k], cp::kTwo, so.cL[k]), sn.cL[k]);
+            const uint32_t gy = cp::hsub(sn.hL[k], so.hL[k]);
+            r.mL[k] = cp::habs_sum(gx, gy);
+            if (!ALIGNED || k == 0 || k == 4) r.mL[k] &= inL[k];
+        }
+        if (yy < 0 || yy >= H) {   // rows above / below the image
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r.mO[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) r.mL[k] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.pO[k] = cp::hadd(r.mO[k], cp::kOne);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r.pL[k] = cp::hadd(r.mL[k], cp::kOne);
+        so = sn;
+        const uint32_t top = cp::umax3(cp::umax3(r.pO[0], r.pO[1], r.pO[2]), r.pO[3], 0u);
+        r.any = cp::hgt_mask(top, low1) != 0u;
+        if (want_sectors && r.any) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp::sector(gxO[k], gyO[k], r.dlo[k], r.dhi[k]);
+        }
+    };
+    uint32_t weak_seen = 0;   // some candidate of this band is not strong: its tile needs hysteresis
+    // output row y from the magnitude rows y-1 (`u`), y (`c`), y+1 (`d`)
+    auto emit = [&](int y, const cp::Mags& u, const cp::Mags& c, const cp::Mags& d) {
+        uint32_t ebyte = 0, cbyte = 0;
+        if (c.any) {
+            uint32_t acc_c = 0, acc_e = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t n_h = cp::umax3(c.pL[k], c.mL[k + 1], low1);      // m > left,  m >= right
+                const uint32_t n_v = cp::umax3(u.pO[k], d.mO[k], low1);          // m > above, m >= below
+                const uint32_t n_d1 = cp::umax3(u.pL[k], d.pL[k + 1], low1);     // (y-1,x-1) / (y+1,x+1)
+                const uint32_t n_d2 = cp::umax3(u.pL[k + 1], d.pL[k], low1);     // (y-1,x+1) / (y+1,x-1)
+                const uint32_t n = cp::bitsel(c.dhi[k], cp::bitsel(c.dlo[k], n_d2, n_d1),
+                                              cp::bitsel(c.dlo[k], n_v, n_h));
+                const uint32_t keep = cp::hgt_mask(c.pO[k], n);
+                const uint32_t strong = keep & cp::hgt_mask(c.pO[k], high1);
+                const uint32_t wk = (1u << (2 * k)) | (2u << (2 * k + 8));       // bit 2k for lane 0, 2k+1 for lane 1
+                acc_c = __dp2a_lo(keep, wk, acc_c);                              // += 65535 * bit
+                acc_e = __dp2a_lo(strong, wk, acc_e);
+            }
+            cbyte = (0u - acc_c) & 0xFFu;   // 65535 b = -b (mod 2^16)
+            ebyte = (0u - acc_e) & 0xFFu;
+        }
+        eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
+        cout[(int64_t)y * row_bytes] = (uint8_t)cbyte;
+        weak_seen |= cbyte & ~ebyte;
+    };
+
+    cp::Sums sa, sb;        // sums of the two most recent rows (roles alternate)
+    cp::Mags r0, r1, r2;    // magnitude rows (roles rotate)
+    {
+        uint32_t w[4];
+        load_window(yb - 2, w);
+        cp::row_sums(w, sa);
+        load_window(yb - 1, w);
+        cp::row_sums(w, sb);
+        advance(yb - 1, sa, sb, r0, false);   // sa: yb-2 -> yb
+        advance(yb, sb, sa, r1, true);        // sb: yb-1 -> yb+1
+    }
+    // entering row y: sa = row y, sb = row y+1, r0 = row y-1, r1 = row y.  Six rows per trip so that the
+    // roles of the two sum sets and the three magnitude rows come back to where they started.
+#pragma unroll 1
+    for (int y = yb; y < ye; y += 6) {
+        advance(y + 1, sa, sb, r2, true);
+        emit(y, r0, r1, r2);
+        if (y + 1 >= ye) break;
+        advance(y + 2, sb, sa, r0, true);
+        emit(y + 1, r1, r2, r0);
+        if (y + 2 >= ye) break;
+        advance(y + 3, sa, sb, r1, true);
+        emit(y + 2, r2, r0, r1);
+        if (y + 3 >= ye) break;
+        advance(y + 4, sb, sa, r2, true);
+        emit(y + 3, r0, r1, r2);
+        if (y + 4 >= ye) break;
+        advance(y + 5, sa, sb, r0, true);
+        emit(y + 4, r1, r2, r0);
+        if (y + 5 >= ye) break;
+        advance(y + 6, sb, sa, r1, true);
+        emit(y + 5, r2, r0, r1);
+    }
+    if (weak_seen) {
+        const int tiles_x = (Wq + 1) / 2;
+        tile_dirty[(f * bands + by) * (int64_t)tiles_x + (x0 >> 6)] = 1;
+    }
+}
+
 // ---- 3. hysteresis on the bit planes ----
 // "Weak pixels 8-connected to an edge pixel become edges" = grow E inside C until nothing changes.
 // A warp owns a 64 x 32 tile: lane r holds row r as one 64-bit word of C and of E.  One step ORs the
@@ -252,6 +434,14 @@ __device__ __forceinline__ unsigned long long run_fill(unsigned long long t, uns
     const unsigned long long dn = __brevll((((cr + tr) ^ cr) & cr) | tr);
     return up | dn;
 }
+
+#if PSD_HYST_STATS   // alt build for tools/gpu_*.sh: per-round tile counts and times of the first launches
+__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512];
+__device__ int g_hs_launch;
+#define HS_COUNT(arr, round) do { if (lane == 0 && (round) < 512) atomicAdd(&arr[round], 1ull); } while (0)
+#else
+#define HS_COUNT(arr, round) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
@@ -287,6 +477,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
             while (todo) {
                 const int64_t t = base + __ffs(todo) - 1;
                 todo &= todo - 1;
+                HS_COUNT(g_hs_visit, round);
                 const int64_t f = t / per_frame_tiles;
                 const int tt = (int)(t - f * per_frame_tiles);
                 const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
@@ -323,6 +514,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 unsigned long long e = (unsigned long long)e_lo | ((unsigned long long)e_hi << 32);
                 // weak pixels left in this tile?  (warp-uniform exit: nothing can change)
                 if (__ballot_sync(0xFFFFFFFFu, (c & ~e) != 0ull) == 0u) continue;
+                HS_COUNT(g_hs_work, round);
                 const uint32_t lbit = e_l >> 31, rbit = e_r & 1u;  // E left of column 0 / right of column 63, this row
                 const unsigned long long e_ring = (unsigned long long)g_lo | ((unsigned long long)g_hi << 32);
                 // the side columns do not change while the tile iterates: fold them into two seed bits per row
@@ -354,6 +546,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 }
                 if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
                     warp_changed = true;
+                    HS_COUNT(g_hs_change, round);
                     // the ring of the 8 neighbours may have changed: they look again next round
                     if (lane < 9 && lane != 4) {
                         const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
@@ -366,7 +559,28 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
         if (warp_changed && lane == 0) atomicOr(&flags[round % 3], 1);
         __threadfence();
         grid.sync();
-        if (*(volatile int32_t*)&flags[round % 3] == 0) break;
+#if PSD_HYST_STATS
+        if (blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            g_hs_time[round] = now;
+        }
+#endif
+        if (*(volatile int32_t*)&flags[round % 3] == 0) {
+#if PSD_HYST_STATS
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const int l = atomicAdd(&g_hs_launch, 1);
+                if (l == 4 || l == 9) {   // a warm launch
+                    printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round + 1, (long long)n_tiles, (int)gridDim.x);
+                    for (int r = 0; r <= round && r < 512; ++r)
+                        printf("  round %d: visited %llu worked %llu changed %llu  +%llu ns\n", r, g_hs_visit[r],
+                               g_hs_work[r], g_hs_change[r], r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
+                }
+                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = 0ull;
+            }
+#endif
+            break;
+        }
     }
 }
 
@@ -407,6 +621,65 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_cols_bits_kernel(const ui
     const int ya = max(y - r, 0), yb = min(y + r, H - 1);
     for (int yy = ya; yy <= yb; ++yy) o |= base[(int64_t)yy * Wq];
     dil[f * per_frame + i] = o;
+}
+
+// rows + columns in one pass for the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a
+// band of kDilBand rows and marches down it with the last 2 R + 1 horizontally dilated rows in registers (the
+// row loop is unrolled 2 R + 1 times so the ring slots are register names).  Saves the round trip of the
+// row-dilated plane and the 2 R + 1 loads per output word of the column kernel.
+constexpr int kDilBand = 32;
+
+template <int R>
+__global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_t* __restrict__ in,
+                                                                   uint32_t* __restrict__ out, int H, int Wq,
+                                                                   int bands, int64_t n_threads,
+                                                                   uint32_t last_word_mask) {
+    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gid >= n_threads) return;
+    const int wq = (int)(gid % Wq);
+    const int band = (int)((gid / Wq) % bands);
+    const int64_t f = gid / ((int64_t)Wq * bands);
+    const uint32_t* src = in + f * (int64_t)H * Wq + wq;
+    uint32_t* dst = out + f * (int64_t)H * Wq + wq;
+    const bool has_prv = wq > 0, has_nxt = wq + 1 < Wq;
+    const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;   // columns >= W stay 0
+    auto hdil = [&](int y) -> uint32_t {
+        if (y < 0 || y >= H) return 0u;
+        const uint32_t* p = src + (int64_t)y * Wq;
+        const uint32_t cur = p[0];
+        const uint32_t prv = has_prv ? p[-1] : 0u;
+        const uint32_t nxt = has_nxt ? p[1] : 0u;
+        uint32_t o = cur;
+#pragma unroll
+        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+        return o & keep;
+    };
+    constexpr int K = 2 * R + 1;
+    uint32_t ring[K];
+    const int y0 = band * kDilBand, y1 = min(y0 + kDilBand, H);
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
+#pragma unroll 1
+    for (int y = y0; y < y1; y += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (y + j < y1) {
+                ring[(K - 1 + j) % K] = hdil(y + j + R);
+                uint32_t o = 0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) o |= ring[i];
+                dst[(int64_t)(y + j) * Wq] = o;
+            }
+        }
+    }
+}
+
+template <int R>
+static void launch_dilate(const uint32_t* in, uint32_t* out, int n, int H, int Wq, uint32_t mask, cudaStream_t stream) {
+    const int bands = (H + kDilBand - 1) / kDilBand;
+    const int64_t n_threads = (int64_t)Wq * bands * n;
+    psd_edge_dilate_bits_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(in, out, H, Wq, bands,
+                                                                                           n_threads, mask);
 }
 
 __global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* __restrict__ dil,
@@ -454,7 +727,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     const int64_t P = (int64_t)W * H;
     const int Wq = (W + 31) / 32;
     const int64_t per_frame = (int64_t)H * Wq;
-    psd_edge_thresholds_kernel<<<(n + 63) / 64, 64, 0, stream>>>(b.vhist, n, P, b.thresholds);
+    psd_edge_thresholds_kernel<<<(n + 7) / 8, 256, 0, stream>>>(b.vhist, n, P, b.thresholds);
     PSD_CHECK_LAUNCH();
     // classify: one thread per 8 columns x kBandRows rows
     {
@@ -467,12 +740,21 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         }
         const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
         PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles0, stream));
+#if PSD_CLASSIFY_PAIRS
+        if ((W & 7) == 0)
+            psd_canny_classify_pairs_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
+                                                                              b.dirty, W, H, Wq, strips, bands, n_threads);
+        else
+            psd_canny_classify_pairs_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
+                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
+#else
         if ((W & 7) == 0)
             psd_canny_classify_bits_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                              b.dirty, W, H, Wq, strips, bands, n_threads);
         else
             psd_canny_classify_bits_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
+#endif
         PSD_CHECK_LAUNCH();
     }
     // hysteresis: one cooperative launch (grid = what is co-resident on the device)
@@ -501,16 +783,30 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     }
     count_launch(3);
     const int r = ksize / 2;
-    psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
-        b.bits_in, b.bits_row, per_frame * n, Wq, r, (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu);
-    PSD_CHECK_LAUNCH();
-    dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
-    psd_edge_dilate_cols_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_row, b.bits_dil, H, Wq, r);
+    const uint32_t last_mask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu;
+    switch (r) {
+        case 1: launch_dilate<1>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 2: launch_dilate<2>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 3: launch_dilate<3>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 4: launch_dilate<4>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 5: launch_dilate<5>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 6: launch_dilate<6>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 7: launch_dilate<7>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 8: launch_dilate<8>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        default: {   // any other kernel size: separable, two launches
+            psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
+                b.bits_in, b.bits_row, per_frame * n, Wq, r, last_mask);
+            PSD_CHECK_LAUNCH();
+            dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
+            psd_edge_dilate_cols_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_row, b.bits_dil, H, Wq, r);
+            count_launch(1);
+        }
+    }
     PSD_CHECK_LAUNCH();
     dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
     psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
     PSD_CHECK_LAUNCH();
-    count_launch(3);
+    count_launch(2);
     PSD_CUDA(cudaMemcpyAsync(b.carry_bits, b.bits_dil + (int64_t)(n - 1) * per_frame,
                              (size_t)per_frame * 4, cudaMemcpyDeviceToDevice, stream));
     return PSD_OK;

@@ -86,6 +86,134 @@ def classify_bits(lum, low, high):
     return E.view("<u4").copy(), C.view("<u4").copy()
 
 
+# ---- the pixel-pair classify kernel (csrc/canny_pairs.cuh): binary16 lanes holding n * 2^-19 ----
+SCALE = np.float16(2.0 ** -19)          # the pattern 0x0020
+
+
+def prmt(a, b, sel):
+    """PTX prmt.b32, default mode: nibble bit 3 = replicate the sign of the selected byte."""
+    src = [(a >> (8 * i)) & 0xFF for i in range(4)] + [(b >> (8 * i)) & 0xFF for i in range(4)]
+    out = 0
+    for i in range(4):
+        nib = (sel >> (4 * i)) & 0xF
+        byte = src[nib & 7]
+        if nib & 8:
+            byte = 0xFF if byte & 0x80 else 0x00
+        out |= byte << (8 * i)
+    return out
+
+
+def funnel_r(lo, hi, sh):
+    return (((hi << 32) | lo) >> sh) & 0xFFFFFFFF
+
+
+def expand_window(w):
+    """canny_pairs.cuh:expand on four window words -> (VO[6], VL[5]) pair patterns."""
+    K = 0x19191919
+    VO = [prmt(w[0], K, 0x4342), prmt(w[1], K, 0x4140), prmt(w[1], K, 0x4342), prmt(w[2], K, 0x4140),
+          prmt(w[2], K, 0x4342), prmt(w[3], K, 0x4140)]
+    s0, s1, s2 = funnel_r(w[0], w[1], 8), funnel_r(w[1], w[2], 8), funnel_r(w[2], w[3], 8)
+    VL = [prmt(s0, K, 0x4342), prmt(s1, K, 0x4140), prmt(s1, K, 0x4342), prmt(s2, K, 0x4140), prmt(s2, K, 0x4342)]
+    return VO, VL
+
+
+def test_pair_expansion_selectors():
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        by = [int(v) for v in rng.integers(0, 256, 16)]          # window bytes, column u = index - 4
+        w = [by[4 * j] | by[4 * j + 1] << 8 | by[4 * j + 2] << 16 | by[4 * j + 3] << 24 for j in range(4)]
+        VO, VL = expand_window(w)
+        col = lambda u: 0x1900 + by[u + 4]
+        for j in range(6):       # VO[j] = columns (2k, 2k+1), k = j - 1
+            k = j - 1
+            assert VO[j] == col(2 * k) | col(2 * k + 1) << 16
+        for k in range(5):       # VL[k] = columns (2k-1, 2k)
+            assert VL[k] == col(2 * k - 1) | col(2 * k) << 16
+    # sign-replicate selectors of the sector masks
+    assert prmt(0x80000000, 0x00000001, 0xFFBB) == 0x0000FFFF
+    assert prmt(0x7FFFFFFF, 0xFFFFFFFF, 0xFFBB) == 0xFFFF0000
+    assert prmt(0x00008000, 0x00008000, 0xBB99) == 0x0000FFFF
+    assert prmt(0x80007FFF, 0x80007FFF, 0xBB99) == 0xFFFF0000
+    # the bit planes' byte from the lane masks: sum of 65535 * weight, negated, low byte
+    for byte in range(256):
+        acc = sum(65535 * (1 << i) for i in range(8) if byte >> i & 1)
+        assert (-acc) & 0xFF == byte
+
+
+def classify_pairs(lum, low, high):
+    """Canny classify with the kernel's number representation: every lane a binary16 value n * 2^-19."""
+    H, W = lum.shape
+    Wq = (W + 31) // 32
+    pad = np.pad(lum, 2, mode="edge").astype(np.uint16)                 # BORDER_REPLICATE, rows/cols -2 .. +1
+    pat = (np.uint16(0x1900) + pad)                                      # 0x1900 + byte
+    val = pat.view(np.float16)                                           # = (1280 + v) * 2^-19
+    assert np.array_equal(val.astype(np.float64) * 2.0 ** 19, 1280.0 + pad)
+    # horizontal sums for columns -1 .. W (index i -> column i - 1), rows -2 .. H+1
+    c = val[:, 2:] - val[:, :-2]                                         # HADD2: exact, the 1280 cancels
+    hbits = (pat[:, :-2] + np.uint16(2) * pat[:, 1:-1] + pat[:, 2:]).astype(np.uint16)   # integer lanes
+    assert hbits.max() < 0x6800
+    hs = hbits.view(np.float16) * SCALE                                  # HMUL2: (1024 + h) * 2^-19
+    assert c.dtype == np.float16 and hs.dtype == np.float16
+    two = np.float16(2.0)
+    gx = (c[1:-1] * two + c[:-2]).astype(np.float16) + c[2:]             # HFMA2 (single rounding of an exact value), HADD2
+    gy = hs[2:] - hs[:-2]
+    m = np.abs(gx) + np.abs(gy)                                          # rows -1 .. H, columns -1 .. W
+    assert m.dtype == np.float16
+    rows = np.arange(-1, H + 1)[:, None]
+    cols = np.arange(-1, W + 1)[None, :]
+    m = np.where((rows >= 0) & (rows < H) & (cols >= 0) & (cols < W), m, np.float16(0))
+    p = m + SCALE
+    # the integers the lanes stand for
+    gi = lambda a: np.rint(a.astype(np.float64) * 2.0 ** 19).astype(np.int64)
+    assert np.array_equal(gi(m) * 2.0 ** -19, m.astype(np.float64))
+    # sectors from the signs of two FP32 FMAs (exact here in float64: 11 x 17 significant bits)
+    ax, ay = np.abs(gx).astype(np.float64), np.abs(gy).astype(np.float64)
+    k22 = float(np.float32(13573.0 / 32768.0))
+    k67 = float(np.float32((13573.0 + 65536.0) / 32768.0))
+    assert k22 * 32768 == 13573 and k67 * 32768 == 79109
+    s22 = (ax * k22 - ay) < 0
+    s67 = (ax * k67 - ay) < 0
+    sxy = np.signbit(gx) != np.signbit(gy)
+    dhi = s22 & ~s67
+    dlo = s67 | (s22 & sxy)
+    # suppression: one comparison per pixel on the unsigned order of the patterns
+    bits = lambda a: a.view(np.uint16).astype(np.int64)
+    mb, pb = bits(m), bits(p)
+    low1 = int(np.float16(np.float32(low + 1) * np.float32(2.0 ** -19)).view(np.uint16))
+    high1 = np.float16(np.float32(high + 1) * np.float32(2.0 ** -19))
+    C_, U_, D_ = slice(1, -1), slice(0, -2), slice(2, None)            # rows y, y-1, y+1
+    X_, Lx, Rx = slice(1, -1), slice(0, -2), slice(2, None)            # columns x, x-1, x+1
+    mx3 = lambda a, b: np.maximum(np.maximum(a, b), low1)
+    n_h = mx3(pb[C_, Lx], mb[C_, Rx])
+    n_v = mx3(pb[U_, X_], mb[D_, X_])
+    n_d1 = mx3(pb[U_, Lx], pb[D_, Rx])
+    n_d2 = mx3(pb[U_, Rx], pb[D_, Lx])
+    hi_, lo_ = dhi[C_, X_], dlo[C_, X_]
+    n = np.where(hi_, np.where(lo_, n_d2, n_d1), np.where(lo_, n_v, n_h))
+    # HSET2.GT compares the VALUES; for non-negative binary16 that is the order of the patterns
+    keep = pb[C_, X_] > n
+    strong = keep & (p[C_, X_] > high1)
+    pack = lambda k: np.packbits(np.pad(k, ((0, 0), (0, Wq * 32 - W))), axis=1, bitorder="little").view("<u4").copy()
+    return pack(strong), pack(keep), gi(gx[C_, X_]), gi(gy[C_, X_])
+
+
+@pytest.mark.parametrize("shape", [(40, 64), (97, 131), (33, 70), (64, 200)])
+def test_pair_lane_classify_equals_integer_classify(shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    hard = rng.integers(0, 2, (h, w), dtype=np.uint8) * 255          # gradients up to +-1020, magnitudes to 2040
+    imgs = [hard, rng.integers(0, 256, (h, w), dtype=np.uint8),
+            cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (5, 5), 0), _snake(h, w)]
+    for lum in imgs:
+        for low, high in (M.canny_thresholds(float(np.median(lum))), (0, 255), (20, 120), (255, 255)):
+            E, C, gx, gy = classify_pairs(lum, low, high)
+            E0, C0 = classify_bits(lum, low, high)
+            assert np.array_equal(C, C0) and np.array_equal(E, E0)
+        sx = cv2.Sobel(lum, cv2.CV_16S, 1, 0, ksize=3, borderType=cv2.BORDER_REPLICATE)
+        sy = cv2.Sobel(lum, cv2.CV_16S, 0, 1, ksize=3, borderType=cv2.BORDER_REPLICATE)
+        assert np.array_equal(gx, sx) and np.array_equal(gy, sy)
+
+
 def hysteresis_bits(E, C, H, W):
     """Rounds over 64x32 tiles exactly as psd_hyst_bits_kernel schedules them; returns (E, rounds)."""
     Wq = E.shape[1]

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP) or not os.path.exi
                                 reason="needs cuobjdump and the built library")
 
 WS_HSV_V7 = "_ZN3psd19psd_score_ws_kernelILj1EEEvNS_9ScoreArgsE"
-CLASSIFY = "_ZN3psd30psd_canny_classify_bits_kernelILb1EEEvPKhPKiPjS5_Phiiiiil"
+CLASSIFY = "_ZN3psd31psd_canny_classify_pairs_kernelILb1EEEvPKhPKiPjS5_Phiiiiil"
 HYST = "_ZN3psd20psd_hyst_bits_kernelEPjPKjPhPiiiiiil"
 LINE = re.compile(r"^\s+/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Za-z0-9_.]+)")
 
@@ -62,13 +62,20 @@ def test_ws_kernel_instruction_mix_and_budget():
 
 
 def test_edge_kernels_use_the_instructions_the_design_names():
-    """classify: Sobel sums by IDP4A on funnel-shifted words, no shared memory, no spills;
+    """classify: 16-bit lane pairs (PRMT expansion, binary16 arithmetic, VIMNMX3 + HSET2 suppression, FP32 FMAs
+    for the sector, IDP.2A bit packing), no shared memory, a per-row instruction budget;
     hysteresis: bit reversal for the downward run fill, a grid barrier (cooperative launch), no spills."""
     rows = sass(CLASSIFY)
     ops = [op for _, op, _ in rows]
-    assert sum(o.startswith("IDP.4A") for o in ops) >= 20 and any(o.startswith("SHF") for o in ops)
+    for needed in ("PRMT", "HFMA2", "HADD2", "HADD2.F32", "FFMA", "VIMNMX3.U16x2", "HSET2.GT", "IDP.2A", "LDG.E.64"):
+        assert any(o.startswith(needed) for o in ops), f"{needed} missing from the classify kernel"
     assert not any(o.startswith(("LDS", "STS", "SHFL", "BAR")) for o in ops)
-    assert sum(o.startswith(("LDL", "STL")) for o in ops) <= 48   # 128-register cap (2 CTAs / SM): a few words spill
+    assert sum(o.startswith(("LDL", "STL")) for o in ops) <= 64   # 128-register cap (2 CTAs / SM): a few words spill
+    # the row loop makes six rows per trip (two sum sets x three magnitude rows): 8 pixels per thread and row
+    body = max((rows[a:b + 1] for a, b in loops(rows)), key=len)
+    assert not any(op.startswith(("I2F", "F2I", "F2F")) for _, op, _ in body)   # no conversion instructions
+    assert sum(op.startswith("STG") for _, op, _ in body) == 12
+    assert len(body) / 6 <= 290, f"classify grew to {len(body) / 6:.0f} instructions per 8-pixel row"
     rows = sass(HYST)
     ops = [op for _, op, _ in rows]
     assert any(o.startswith("BREV") for o in ops) and any(o.startswith("SHFL") for o in ops)

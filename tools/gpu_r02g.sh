@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call G: weak-candidate tile flags from classify, I2F lift A/B, edge launch list
+# round 2, call G: pixel-pair classify kernel vs the 32-bit one, weak-candidate tile flags, I2F lift A/B, edge launch list
 O=gpurun_out/r02g; mkdir -p $O
 timeout 900 python -m pytest tests -q -m gpu > $O/pytest_gpu.txt 2>&1; tail -8 $O/pytest_gpu.txt
 L=pyscenedetect_b200/libpsd_b200.so; cp $L /tmp/orig.so
@@ -8,7 +8,9 @@ run default
 for a in pyscenedetect_b200/csrc/build/alt_*.so; do [ -f "$a" ] || continue; t=$(basename $a .so); cp $a $L; run $t; done
 cp /tmp/orig.so $L
 run default2
-timeout 300 python bench.py --detector content_edges --frames 4096 --steps 5 --warmup 3 --no-cpu --no-e2e > $O/bench_content_edges.json 2> $O/bench_content_edges.err
+edges() { timeout 300 python bench.py --detector content_edges --frames 4096 --steps 5 --warmup 3 --no-cpu --no-e2e > $O/bench_content_edges_$1.json 2> $O/bench_content_edges_$1.err; }
+edges pairs
+cp pyscenedetect_b200/csrc/build/edgealt_old.so $L; edges oldclassify; cp /tmp/orig.so $L
 for f in $O/bench_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
