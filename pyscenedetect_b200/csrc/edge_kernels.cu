@@ -26,9 +26,6 @@ namespace cg = cooperative_groups;
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
 #endif
-#ifndef PSD_CLASSIFY_PAIRS
-#define PSD_CLASSIFY_PAIRS 1
-#endif
 
 namespace psd {
 
@@ -78,190 +75,20 @@ __global__ void psd_edge_thresholds_kernel(const uint32_t* __restrict__ vhist, i
 }
 
 // ---- 2. Sobel + L1 magnitude + NMS + double threshold -> bit planes ----
-// One thread owns 8 consecutive columns (one byte of each bit plane per row) and marches down a band
-// of kBandRows rows; everything it needs from neighbouring rows stays in registers.  Per row it pulls
-// the 16 bytes around its columns (x0-4 .. x0+11) and forms, for the 10 columns x0-1 .. x0+8,
-//     h(i) = V(i-1) + 2 V(i) + V(i+1)      (IDP4A with weights 1,2,1)
-//     c(i) = V(i+1) - V(i-1)               (IDP4A with weights -1,0,1)
-// after one funnel shift that moves bytes i-1..i+1 to the bottom of a word.  Sobel is then vertical
-// arithmetic on those sums:  gx = c(y-1) + 2 c(y) + c(y+1),  gy = h(y+1) - h(y-1); two rows of sums,
-// three rows of magnitudes and the 2-bit direction sector of the pixels above the low threshold are all the
-// state.  No shared memory, no shuffles, no barrier; neighbouring threads re-read overlapping words from L1.
+// One thread owns 8 consecutive columns (one byte of each bit plane per row) and marches down a band of
+// kBandRows rows; everything it needs from neighbouring rows stays in registers.  The arithmetic is done on
+// pixel PAIRS, two 16-bit lanes per register (canny_pairs.cuh).  No shared memory, no shuffles, no barrier;
+// neighbouring threads re-read overlapping words from L1.  (Round 2's first version of this kernel kept one
+// pixel per 32-bit register - IDP4A row sums, integer NMS: 476 instructions per 8-pixel row against 281,
+// profiles/r02i_edge_ab_summary.txt.)
+//
+// The two planes it writes are TILE-MAJOR: tile (ty, tx) = rows 32 ty .. 32 ty + 31 x columns 64 tx .. 64 tx + 63
+// is 64 consecutive words, row r of the tile at words 2 r and 2 r + 1.  A warp of the hysteresis kernel then
+// pulls its whole tile with one 256-byte request instead of 32 row fragments 4 Wq bytes apart.  Words and
+// rows beyond the image are never written by anyone and stay 0 from the allocation.
 constexpr int kBandRows = 32;   // == kHystTileH: a band of the classify kernel is one tile row of the hysteresis
+constexpr int kTileWords = 64;  // 32 rows x 2 words
 
-// sum of (unsigned byte of a) x (signed byte of b): the C++ __dp4a overloads are all-signed or all-unsigned
-__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b) {
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
-    return d;
-}
-
-template <bool ALIGNED>
-__global__ void __launch_bounds__(256, 2) psd_canny_classify_bits_kernel(
-    const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
-    uint32_t* __restrict__ cand_bits, uint8_t* __restrict__ tile_dirty, int W, int H, int Wq, int strips,
-    int bands, int64_t n_threads) {
-    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (gid >= n_threads) return;
-    const int sx = (int)(gid % strips);
-    const int by = (int)((gid / strips) % bands);
-    const int64_t f = gid / ((int64_t)strips * bands);
-    const int64_t P = (int64_t)W * H;
-    const uint8_t* src = vplane + f * P;
-    uint8_t* eout = reinterpret_cast<uint8_t*>(edge_bits + f * (int64_t)H * Wq) + sx;
-    uint8_t* cout = reinterpret_cast<uint8_t*>(cand_bits + f * (int64_t)H * Wq) + sx;
-    const int low = thr[2 * f], high = thr[2 * f + 1];
-    const int x0 = sx * 8;
-    const int yb = by * kBandRows, ye = min(yb + kBandRows, H);
-    const int row_bytes = Wq * 4;
-    // columns (of the 10 gradient columns) that lie inside the image: gradients outside are zero
-    uint32_t col_in = 0;
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-        if (x0 - 1 + i >= 0 && x0 - 1 + i < W) col_in |= 1u << i;
-
-    // the 16 bytes x0-4 .. x0+11 of row y (BORDER_REPLICATE in both directions)
-    auto load_window = [&](int y, uint32_t (&w)[4]) {
-        const int yc = min(max(y, 0), H - 1);
-        const uint8_t* row = src + (int64_t)yc * W;
-        if (ALIGNED) {  // W % 8 == 0: every strip is whole, words are 4-byte aligned
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(row) + 2 * sx;
-            w[1] = rw[0];
-            w[2] = rw[1];
-            w[0] = (sx > 0) ? rw[-1] : __byte_perm(w[1], 0, 0x0000);        // replicate column 0
-            w[3] = (x0 + 8 < W) ? rw[2] : __byte_perm(w[2], 0, 0x3333);     // replicate column W-1
-        } else {
-            w[0] = w[1] = w[2] = w[3] = 0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int x = min(max(x0 - 4 + k, 0), W - 1);
-                w[k >> 2] |= (uint32_t)row[x] << (8 * (k & 3));
-            }
-        }
-    };
-    // horizontal sums of gradient column i (x0-1+i) from a window: its left neighbour is window byte 2+i
-    auto col_sums = [&](const uint32_t (&w)[4], int i, int& h, int& c) {
-        const int b = 2 + i;
-        const uint32_t t = __funnelshift_r(w[b >> 2], w[(b >> 2) + 1 > 3 ? 3 : (b >> 2) + 1], 8 * (b & 3));
-        h = __dp4a(t, 0x00010201u, 0u);   // V(i-1) + 2 V(i) + V(i+1)
-        c = dp4a_u8_s8(t, 0x000100FFu);   // V(i+1) - V(i-1)   (signed weights -1, 0, +1)
-    };
-
-    uint32_t weak_seen = 0;               // some candidate of this band is not strong: its tile needs hysteresis
-    int cA[10], cB[10], hA[10], hB[10];   // sums of the two most recent rows (roles alternate)
-    int mU[10], mC[10], mD[10];           // magnitudes of rows y-1, y, y+1
-    // direction sectors of the 8 output columns of rows y / y+1 as two 8-bit masks (OpenCV's fixed-point
-    // tangent test): (hi, lo) = 00 compare left/right, 01 up/down, 10 the (y-1,x-1)/(y+1,x+1) diagonal,
-    // 11 the (y-1,x+1)/(y+1,x-1) diagonal
-    uint32_t dloC = 0, dhiC = 0, dloD = 0, dhiD = 0;
-    // Row `yy+1` arrives: gradient of row yy from rows yy-1 (`co`/`ho`, overwritten with row yy+1 on the way
-    // out), yy (`cm`) and yy+1.  Magnitudes go to `m`, sectors to (dlo, dhi) if some pixel can be a candidate.
-    auto advance = [&](int yy, int (&co)[10], const int (&cm)[10], int (&ho)[10], int (&m)[10], uint32_t& dlo,
-                       uint32_t& dhi) {
-        uint32_t w[4];
-        load_window(yy + 1, w);
-        int gxs[8], gys[8];
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            int hn, cn;
-            col_sums(w, i, hn, cn);
-            const int gx = co[i] + 2 * cm[i] + cn;
-            const int gy = hn - ho[i];
-            co[i] = cn;
-            ho[i] = hn;
-            m[i] = abs(gx) + abs(gy);
-            if (i >= 1 && i <= 8) { gxs[i - 1] = gx; gys[i - 1] = gy; }
-        }
-        // gradients outside the image are zero (cv2 pads the magnitude buffer): whole rows above / below the
-        // image, and the columns left / right of it (only the first / last strip has any)
-        if (yy < 0 || yy >= H) {
-#pragma unroll
-            for (int i = 0; i < 10; ++i) m[i] = 0;
-        }
-        if (ALIGNED) {
-            if (sx == 0) m[0] = 0;
-            if (x0 + 8 >= W) m[9] = 0;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 10; ++i)
-                if (!((col_in >> i) & 1u)) m[i] = 0;
-        }
-#pragma unroll
-        for (int i = 1; i <= 8; ++i) any |= m[i] > low;
-        dlo = dhi = 0;
-        if (any) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int ax = abs(gxs[i]), ay = abs(gys[i]);
-                const int t22 = ax * 13573 - (ay << 15);        // > 0  <=>  ay*2^15 < tg22 * ax
-                const int t67 = t22 + (ax << 16);               // < 0  <=>  ay*2^15 > tg67 * ax
-                const bool horiz = t22 > 0, vert = t67 < 0;
-                const bool diag = !horiz && !vert;
-                if (diag) dhi |= 1u << i;
-                if (vert || (diag && ((gxs[i] ^ gys[i]) < 0))) dlo |= 1u << i;
-            }
-        }
-    };
-    // prologue: rows yb-2, yb-1 into (A, B); gradients of rows yb-1 and yb
-    {
-        uint32_t w[4];
-        load_window(yb - 2, w);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) col_sums(w, i, hA[i], cA[i]);
-        load_window(yb - 1, w);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) col_sums(w, i, hB[i], cB[i]);
-        uint32_t u0, u1;
-        advance(yb - 1, cA, cB, hA, mU, u0, u1);   // A: yb-2 -> yb
-        advance(yb, cB, cA, hB, mC, dloC, dhiC);   // B: yb-1 -> yb+1
-    }
-    // one output row y: on entry (co, ho) hold row y, (cm) row y+1
-    auto row_step = [&](int y, int (&co)[10], const int (&cm)[10], int (&ho)[10]) {
-        advance(y + 1, co, cm, ho, mD, dloD, dhiD);
-        uint32_t ebyte = 0, cbyte = 0;
-        bool any = false;
-#pragma unroll
-        for (int i = 1; i <= 8; ++i) any |= mC[i] > low;
-        if (any) {
-            // the four non-maximum tests of every pixel as bit masks, then one mask expression picks by sector
-            uint32_t kH = 0, kV = 0, kD1 = 0, kD2 = 0, above = 0, strong = 0;
-#pragma unroll
-            for (int i = 1; i <= 8; ++i) {
-                const int m = mC[i];
-                const uint32_t bit = 1u << (i - 1);
-                if (m > mC[i - 1] && m >= mC[i + 1]) kH |= bit;
-                if (m > mU[i] && m >= mD[i]) kV |= bit;
-                if (m > mU[i - 1] && m > mD[i + 1]) kD1 |= bit;
-                if (m > mU[i + 1] && m > mD[i - 1]) kD2 |= bit;
-                if (m > low) above |= bit;
-                if (m > high) strong |= bit;
-            }
-            const uint32_t keep = ((~dhiC & ~dloC & kH) | (~dhiC & dloC & kV) | (dhiC & ~dloC & kD1) | (dhiC & dloC & kD2)) & above;
-            cbyte = keep & 0xFFu;
-            ebyte = keep & strong & 0xFFu;
-        }
-        eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
-        cout[(int64_t)y * row_bytes] = (uint8_t)cbyte;
-        weak_seen |= cbyte & ~ebyte;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) { mU[i] = mC[i]; mC[i] = mD[i]; }
-        dloC = dloD; dhiC = dhiD;
-    };
-    // after the prologue: A holds row yb, B row yb+1
-#pragma unroll 1
-    for (int y = yb; y < ye; y += 2) {
-        row_step(y, cA, cB, hA);
-        if (y + 1 < ye) row_step(y + 1, cB, cA, hB);
-    }
-    // a band is exactly one hysteresis tile row high (kBandRows == kHystTileH) and 8 of its 64 columns wide
-    if (weak_seen) {
-        const int tiles_x = (Wq + 1) / 2;
-        tile_dirty[(f * bands + by) * (int64_t)tiles_x + (x0 >> 6)] = 1;
-    }
-}
-
-// ---- 2b. the same stage on pixel pairs (canny_pairs.cuh): two 16-bit lanes per register ----
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
@@ -274,12 +101,14 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
     const int64_t f = gid / ((int64_t)strips * bands);
     const int64_t P = (int64_t)W * H;
     const uint8_t* src = vplane + f * P;
-    uint8_t* eout = reinterpret_cast<uint8_t*>(edge_bits + f * (int64_t)H * Wq) + sx;
-    uint8_t* cout = reinterpret_cast<uint8_t*>(cand_bits + f * (int64_t)H * Wq) + sx;
+    // this band's tile of the planes: byte (sx & 7) of each of its 32 rows (8 bytes per row)
+    const int tiles_x = (Wq + 1) / 2;
+    const int64_t tile = (f * bands + by) * (int64_t)tiles_x + (sx >> 3);
+    const int yb = by * kBandRows, ye = min(yb + kBandRows, H);
+    uint8_t* eout = reinterpret_cast<uint8_t*>(edge_bits + tile * kTileWords) + (sx & 7) - (int64_t)yb * 8;
+    uint8_t* cout = reinterpret_cast<uint8_t*>(cand_bits + tile * kTileWords) + (sx & 7) - (int64_t)yb * 8;
     const uint32_t low1 = cp::scaled2(thr[2 * f] + 1), high1 = cp::scaled2(thr[2 * f + 1] + 1);
     const int x0 = sx * 8;
-    const int yb = by * kBandRows, ye = min(yb + kBandRows, H);
-    const int row_bytes = Wq * 4;
     // lanes of the pairs that lie inside the image (gradients outside are zero: cv2 pads the magnitude buffer)
     uint32_t inO[4], inL[5];
 #pragma unroll
@@ -314,6 +143,9 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
     auto advance = [&](int yy, cp::Sums& so, const cp::Sums& sm, cp::Mags& r, bool want_sectors) {
         uint32_t w[4];
         load_window(yy + 1, w);
+        // the first touch of a row goes to L2 / HBM and four warps per scheduler cannot hide that: pull the line
+        // of the row two further down into L1 now (no register, no dependency; +4 % on the edge path)
+        if (yy + 3 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (int64_t)(yy + 3) * W + x0));
         cp::Sums sn;
         cp::row_sums(w, sn);
         uint32_t gxO[4], gyO[4];
@@ -372,8 +204,8 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
             cbyte = (0u - acc_c) & 0xFFu;   // 65535 b = -b (mod 2^16)
             ebyte = (0u - acc_e) & 0xFFu;
         }
-        eout[(int64_t)y * row_bytes] = (uint8_t)ebyte;
-        cout[(int64_t)y * row_bytes] = (uint8_t)cbyte;
+        eout[y * 8] = (uint8_t)ebyte;
+        cout[y * 8] = (uint8_t)cbyte;
         weak_seen |= cbyte & ~ebyte;
     };
 
@@ -410,10 +242,7 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
         advance(y + 6, sb, sa, r1, true);
         emit(y + 5, r2, r0, r1);
     }
-    if (weak_seen) {
-        const int tiles_x = (Wq + 1) / 2;
-        tile_dirty[(f * bands + by) * (int64_t)tiles_x + (x0 >> 6)] = 1;
-    }
+    if (weak_seen) tile_dirty[tile] = 1;
 }
 
 // ---- 3. hysteresis on the bit planes ----
@@ -436,7 +265,7 @@ __device__ __forceinline__ unsigned long long run_fill(unsigned long long t, uns
 }
 
 #if PSD_HYST_STATS   // alt build for tools/gpu_*.sh: per-round tile counts and times of the first launches
-__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512];
+__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512];
 __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { if (lane == 0 && (round) < 512) atomicAdd(&arr[round], 1ull); } while (0)
 #else
@@ -453,7 +282,6 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t per_frame_tiles = (int64_t)tiles_x * tiles_y;
-    const int64_t frame_words = (int64_t)H * Wq;
     // a warp owns a contiguous run of tiles: their dirty bytes are read 32 at a time, one per lane
     const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
     const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles);
@@ -481,34 +309,27 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 const int64_t f = t / per_frame_tiles;
                 const int tt = (int)(t - f * per_frame_tiles);
                 const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-                const int y0 = ty * kHystTileH, wq0 = tx * 2;
-                const int y = y0 + lane;
-                uint32_t* E = edge_bits + f * frame_words;
-                const uint32_t* C = cand_bits + f * frame_words;
-                const bool row_in = y < H;
-                const bool has_w1 = wq0 + 1 < Wq;
-                const bool has_left = wq0 > 0, has_right = wq0 + 2 < Wq;
-                // every load of the tile and of its ring is issued before the first use
-                uint32_t c_lo = 0, c_hi = 0, e_lo = 0, e_hi = 0, e_l = 0, e_r = 0;
-                if (row_in) {
-                    const uint32_t* pc = C + (int64_t)y * Wq + wq0;
-                    const uint32_t* pe = E + (int64_t)y * Wq + wq0;
-                    c_lo = pc[0];
-                    e_lo = pe[0];
-                    if (has_w1) { c_hi = pc[1]; e_hi = pe[1]; }
-                    if (has_left) e_l = pe[-1];
-                    if (has_right) e_r = pe[2];
-                }
-                // ring rows above / below the tile: lane 0 / lane 31 fetch them
-                const int ring_y = (lane == 0) ? y0 - 1 : y0 + kHystTileH;
-                const bool ring_in = (lane == 0 && y0 > 0) || (lane == 31 && y0 + kHystTileH < H);
+                uint32_t* Et = edge_bits + t * kTileWords;            // tile-major planes: 64 words per tile
+                const uint32_t* Ct = cand_bits + t * kTileWords;
+                const bool has_left = tx > 0, has_right = tx + 1 < tiles_x;
+                // every load of the tile and of its ring is issued before the first use.  Rows beyond the image
+                // and the second word of a last odd column hold 0 in both planes.
+                const uint2 cw = reinterpret_cast<const uint2*>(Ct)[lane];
+                const uint2 ew = reinterpret_cast<const uint2*>(Et)[lane];
+                const uint32_t c_lo = cw.x, c_hi = cw.y, e_lo = ew.x, e_hi = ew.y;
+                const uint32_t e_l = has_left ? Et[-kTileWords + 2 * lane + 1] : 0u;   // word 1 of the left tile
+                const uint32_t e_r = has_right ? Et[kTileWords + 2 * lane] : 0u;       // word 0 of the right tile
+                // ring rows above / below the tile: lane 0 / lane 31 fetch them (row 31 of the tile above,
+                // row 0 of the tile below)
+                const bool ring_in = (lane == 0 && ty > 0) || (lane == 31 && ty + 1 < tiles_y);
                 uint32_t g_lo = 0, g_hi = 0, g_l = 0, g_r = 0;
                 if (ring_in) {
-                    const uint32_t* pe = E + (int64_t)ring_y * Wq + wq0;
+                    const uint32_t* pe = (lane == 0) ? Et - (int64_t)tiles_x * kTileWords + 62
+                                                     : Et + (int64_t)tiles_x * kTileWords;
                     g_lo = pe[0];
-                    if (has_w1) g_hi = pe[1];
-                    if (has_left) g_l = pe[-1];
-                    if (has_right) g_r = pe[2];
+                    g_hi = pe[1];
+                    if (has_left) g_l = pe[-kTileWords + 1];
+                    if (has_right) g_r = pe[kTileWords];
                 }
                 const unsigned long long c = (unsigned long long)c_lo | ((unsigned long long)c_hi << 32);
                 unsigned long long e = (unsigned long long)e_lo | ((unsigned long long)e_hi << 32);
@@ -527,6 +348,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 if (ru | rbit | rd) side_seed |= 1ull << 63;
                 const unsigned long long e_in = e;
                 while (true) {
+                    HS_COUNT(g_hs_iter, round);
                     unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, e, 1), d = __shfl_down_sync(0xFFFFFFFFu, e, 1);
                     if (lane == 0) u = e_ring;
                     if (lane == 31) d = e_ring;
@@ -539,11 +361,7 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                     if (__ballot_sync(0xFFFFFFFFu, ch) == 0u) break;
                 }
                 const bool changed = e != e_in;
-                if (changed && row_in) {
-                    uint32_t* p = E + (int64_t)y * Wq + wq0;
-                    if ((uint32_t)e != (uint32_t)e_in) p[0] = (uint32_t)e;
-                    if (has_w1 && (uint32_t)(e >> 32) != (uint32_t)(e_in >> 32)) p[1] = (uint32_t)(e >> 32);
-                }
+                if (changed) reinterpret_cast<uint2*>(Et)[lane] = make_uint2((uint32_t)e, (uint32_t)(e >> 32));
                 if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
                     warp_changed = true;
                     HS_COUNT(g_hs_change, round);
@@ -573,10 +391,11 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 if (l == 4 || l == 9) {   // a warm launch
                     printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round + 1, (long long)n_tiles, (int)gridDim.x);
                     for (int r = 0; r <= round && r < 512; ++r)
-                        printf("  round %d: visited %llu worked %llu changed %llu  +%llu ns\n", r, g_hs_visit[r],
-                               g_hs_work[r], g_hs_change[r], r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
+                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  +%llu ns\n", r,
+                               g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
+                               r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
                 }
-                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = 0ull;
+                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
             }
 #endif
             break;
@@ -585,53 +404,56 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
 }
 
 // ---- 4. dilate on the bit-packed edge maps, SAD ----
-// rows: out = OR over |dx| <= r of the row shifted by dx (funnel shifts across word boundaries)
-__global__ void __launch_bounds__(256) psd_edge_dilate_rows_bits_kernel(const uint32_t* __restrict__ in,
-                                                                        uint32_t* __restrict__ out,
-                                                                        int64_t n_words, int Wq, int r,
-                                                                        uint32_t last_word_mask) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
-    const int wq = (int)(i % Wq);
-    const uint32_t cur = in[i];
-    const uint32_t prv = (wq > 0) ? in[i - 1] : 0u;
-    const uint32_t nxt = (wq + 1 < Wq) ? in[i + 1] : 0u;
-    uint32_t o = cur;
-    for (int s = 1; s <= r; ++s) {
-        o |= __funnelshift_r(cur, nxt, s);  // pixel x+s -> bit position of x
-        o |= __funnelshift_l(prv, cur, s);  // pixel x-s
-    }
-    // columns >= W of the last word must stay 0: the SAD counts whole words (found by the 131x97 case
-    // of test_edge_intermediates_match_cv2: dilation spilled into the padding bits)
-    if (wq == Wq - 1) o &= last_word_mask;
-    out[i] = o;
+// The edge plane arrives tile-major (section 2); the dilated plane is row-major [n][H][Wq].
+__device__ __forceinline__ uint32_t tiled_word(const uint32_t* __restrict__ plane, int tiles_x, int y, int wq) {
+    return plane[((int64_t)(y >> 5) * tiles_x + (wq >> 1)) * kTileWords + ((y & 31) << 1) + (wq & 1)];
 }
 
-// columns + SAD: dil[y] = OR over |dy| <= r of rows[y+dy]; count differing pixels vs previous frame
-__global__ void __launch_bounds__(256) psd_edge_dilate_cols_bits_kernel(const uint32_t* __restrict__ rows,
-                                                                        uint32_t* __restrict__ dil, int H,
-                                                                        int Wq, int r) {
+// one row of one word column, horizontally dilated: OR over |dx| <= r of the row shifted by dx (funnel shifts
+// across word boundaries); columns >= W of the last word stay 0 (the SAD counts whole words)
+template <int R>
+__device__ __forceinline__ uint32_t hdil_word(const uint32_t* __restrict__ plane, int tiles_x, int Wq, int y, int wq,
+                                              int r, uint32_t keep) {
+    const uint32_t cur = tiled_word(plane, tiles_x, y, wq);
+    const uint32_t prv = (wq > 0) ? tiled_word(plane, tiles_x, y, wq - 1) : 0u;
+    const uint32_t nxt = (wq + 1 < Wq) ? tiled_word(plane, tiles_x, y, wq + 1) : 0u;
+    uint32_t o = cur;
+    if (R > 0) {
+#pragma unroll
+        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+    } else {
+        for (int s = 1; s <= r; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+    }
+    return o & keep;
+}
+
+// any kernel size: one thread per output word, (2 r + 1) x 3 loads
+__global__ void __launch_bounds__(256) psd_edge_dilate_any_bits_kernel(const uint32_t* __restrict__ in,
+                                                                       uint32_t* __restrict__ dil, int H, int Wq,
+                                                                       int tiles_x, int64_t tile_words_per_frame,
+                                                                       int r, uint32_t last_word_mask) {
     const int64_t per_frame = (int64_t)H * Wq;
     const int64_t f = blockIdx.y;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= per_frame) return;
     const int y = (int)(i / Wq), wq = (int)(i - (int64_t)y * Wq);
-    const uint32_t* base = rows + f * per_frame + wq;
+    const uint32_t* src = in + f * tile_words_per_frame;
+    const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;
     uint32_t o = 0;
     const int ya = max(y - r, 0), yb = min(y + r, H - 1);
-    for (int yy = ya; yy <= yb; ++yy) o |= base[(int64_t)yy * Wq];
+    for (int yy = ya; yy <= yb; ++yy) o |= hdil_word<0>(src, tiles_x, Wq, yy, wq, r, keep);
     dil[f * per_frame + i] = o;
 }
 
-// rows + columns in one pass for the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a
-// band of kDilBand rows and marches down it with the last 2 R + 1 horizontally dilated rows in registers (the
-// row loop is unrolled 2 R + 1 times so the ring slots are register names).  Saves the round trip of the
-// row-dilated plane and the 2 R + 1 loads per output word of the column kernel.
+// the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a band of kDilBand rows and
+// marches down it with the last 2 R + 1 horizontally dilated rows in registers (the row loop is unrolled
+// 2 R + 1 times so the ring slots are register names): 3 loads per output word.
 constexpr int kDilBand = 32;
 
 template <int R>
 __global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_t* __restrict__ in,
                                                                    uint32_t* __restrict__ out, int H, int Wq,
+                                                                   int tiles_x, int64_t tile_words_per_frame,
                                                                    int bands, int64_t n_threads,
                                                                    uint32_t last_word_mask) {
     const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -639,20 +461,12 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_
     const int wq = (int)(gid % Wq);
     const int band = (int)((gid / Wq) % bands);
     const int64_t f = gid / ((int64_t)Wq * bands);
-    const uint32_t* src = in + f * (int64_t)H * Wq + wq;
+    const uint32_t* src = in + f * tile_words_per_frame;
     uint32_t* dst = out + f * (int64_t)H * Wq + wq;
-    const bool has_prv = wq > 0, has_nxt = wq + 1 < Wq;
     const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;   // columns >= W stay 0
     auto hdil = [&](int y) -> uint32_t {
         if (y < 0 || y >= H) return 0u;
-        const uint32_t* p = src + (int64_t)y * Wq;
-        const uint32_t cur = p[0];
-        const uint32_t prv = has_prv ? p[-1] : 0u;
-        const uint32_t nxt = has_nxt ? p[1] : 0u;
-        uint32_t o = cur;
-#pragma unroll
-        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
-        return o & keep;
+        return hdil_word<R>(src, tiles_x, Wq, y, wq, R, keep);
     };
     constexpr int K = 2 * R + 1;
     uint32_t ring[K];
@@ -677,9 +491,11 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_
 template <int R>
 static void launch_dilate(const uint32_t* in, uint32_t* out, int n, int H, int Wq, uint32_t mask, cudaStream_t stream) {
     const int bands = (H + kDilBand - 1) / kDilBand;
+    const int tiles_x = (Wq + 1) / 2;
+    const int64_t tile_words = (int64_t)tiles_x * ((H + kHystTileH - 1) / kHystTileH) * kTileWords;
     const int64_t n_threads = (int64_t)Wq * bands * n;
-    psd_edge_dilate_bits_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(in, out, H, Wq, bands,
-                                                                                           n_threads, mask);
+    psd_edge_dilate_bits_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(
+        in, out, H, Wq, tiles_x, tile_words, bands, n_threads, mask);
 }
 
 __global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* __restrict__ dil,
@@ -705,18 +521,25 @@ __global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* 
     }
 }
 
-// debug/test tap: bit-packed map -> 0/255 bytes
+// debug/test tap: bit-packed map (row-major, or tile-major if tiles_x > 0) -> 0/255 bytes
 __global__ void psd_edge_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __restrict__ out, int W,
-                                       int H, int Wq) {
+                                       int H, int Wq, int tiles_x) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)W * H) return;
     const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
-    out[i] = ((bits[(int64_t)y * Wq + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+    const uint32_t w = tiles_x > 0 ? tiled_word(bits, tiles_x, y, x >> 5) : bits[(int64_t)y * Wq + (x >> 5)];
+    out[i] = ((w >> (x & 31)) & 1u) ? 255 : 0;
 }
 
-int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, cudaStream_t stream) {
+int64_t edge_tile_words(int W, int H) {
     const int Wq = (W + 31) / 32;
-    psd_edge_unpack_kernel<<<(unsigned)(((int64_t)W * H + 255) / 256), 256, 0, stream>>>(bits, out, W, H, Wq);
+    return (int64_t)((Wq + 1) / 2) * ((H + kHystTileH - 1) / kHystTileH) * kTileWords;
+}
+
+int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, bool tile_major, cudaStream_t stream) {
+    const int Wq = (W + 31) / 32;
+    psd_edge_unpack_kernel<<<(unsigned)(((int64_t)W * H + 255) / 256), 256, 0, stream>>>(bits, out, W, H, Wq,
+                                                                                         tile_major ? (Wq + 1) / 2 : 0);
     PSD_CHECK_LAUNCH();
     return PSD_OK;
 }
@@ -734,27 +557,16 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         const int strips = (W + 7) / 8, bands = (H + kBandRows - 1) / kBandRows;
         const int64_t n_threads = (int64_t)strips * bands * n;
         const unsigned blocks = (unsigned)((n_threads + 255) / 256);
-        if (W & 31) {  // the last word of a row has bytes no strip writes: they must read 0
-            PSD_CUDA(cudaMemsetAsync(b.bits_in, 0, (size_t)per_frame * 4 * n, stream));
-            PSD_CUDA(cudaMemsetAsync(b.cand, 0, (size_t)per_frame * 4 * n, stream));
-        }
+        // (bytes of the planes that no strip writes - beyond the last strip, below the last row - were zeroed
+        // when the planes were allocated and nothing ever sets them)
         const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
         PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles0, stream));
-#if PSD_CLASSIFY_PAIRS
         if ((W & 7) == 0)
             psd_canny_classify_pairs_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
         else
             psd_canny_classify_pairs_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                                b.dirty, W, H, Wq, strips, bands, n_threads);
-#else
-        if ((W & 7) == 0)
-            psd_canny_classify_bits_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
-                                                                             b.dirty, W, H, Wq, strips, bands, n_threads);
-        else
-            psd_canny_classify_bits_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
-                                                                              b.dirty, W, H, Wq, strips, bands, n_threads);
-#endif
         PSD_CHECK_LAUNCH();
     }
     // hysteresis: one cooperative launch (grid = what is co-resident on the device)
@@ -793,13 +605,10 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         case 6: launch_dilate<6>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
         case 7: launch_dilate<7>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
         case 8: launch_dilate<8>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        default: {   // any other kernel size: separable, two launches
-            psd_edge_dilate_rows_bits_kernel<<<(unsigned)((per_frame * n + 255) / 256), 256, 0, stream>>>(
-                b.bits_in, b.bits_row, per_frame * n, Wq, r, last_mask);
-            PSD_CHECK_LAUNCH();
+        default: {   // any other kernel size
             dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
-            psd_edge_dilate_cols_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_row, b.bits_dil, H, Wq, r);
-            count_launch(1);
+            psd_edge_dilate_any_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_in, b.bits_dil, H, Wq, (Wq + 1) / 2,
+                                                                     edge_tile_words(W, H), r, last_mask);
         }
     }
     PSD_CHECK_LAUNCH();

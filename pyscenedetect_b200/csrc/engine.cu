@@ -277,7 +277,7 @@ void psd_engine_destroy(psd_engine* e) {
     cudaFree(e->carry); cudaFree(e->d_sums); cudaFree(e->d_yhist); cudaFree(e->d_hash);
     hash_plan_destroy(&e->hash);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.cand);
-    cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_row); cudaFree(e->eb.bits_dil);
+    cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_dil);
     cudaFree(e->eb.carry_bits); cudaFree(e->eb.dirty); cudaFree(e->eb.hyst_flags);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -369,10 +369,14 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         const size_t plane = (size_t)e->P * e->max_batch;
         ENG_CUDA(cudaMalloc(&e->eb.vplane, plane));
         const size_t words = (size_t)e->H * ((e->W + 31) / 32);
-        ENG_CUDA(cudaMalloc(&e->eb.cand, words * 4 * e->max_batch));
+        // the two planes of the hysteresis are tile-major and padded to whole 64 x 32 tiles; the padding is never
+        // written, so it is zeroed once here
+        const size_t tiled = (size_t)edge_tile_words(e->W, e->H) * 4 * e->max_batch;
+        ENG_CUDA(cudaMalloc(&e->eb.cand, tiled));
+        ENG_CUDA(cudaMalloc(&e->eb.bits_in, tiled));
+        ENG_CUDA(cudaMemset(e->eb.cand, 0, tiled));
+        ENG_CUDA(cudaMemset(e->eb.bits_in, 0, tiled));
         ENG_CUDA(cudaMalloc(&e->eb.tmp, (size_t)e->P));
-        ENG_CUDA(cudaMalloc(&e->eb.bits_in, words * 4 * e->max_batch));
-        ENG_CUDA(cudaMalloc(&e->eb.bits_row, words * 4 * e->max_batch));
         ENG_CUDA(cudaMalloc(&e->eb.bits_dil, words * 4 * e->max_batch));
         ENG_CUDA(cudaMalloc(&e->eb.carry_bits, words * 4));
         ENG_CUDA(cudaMalloc(&e->eb.vhist, (size_t)e->max_batch * 256 * 4));
@@ -617,8 +621,9 @@ int psd_engine_debug_plane(psd_engine* e, int which, int64_t index, uint8_t* out
     PSD_REQUIRE(which >= 1 && which <= 3, "unknown plane %d", which);
     if (which == 2 || which == 3) {  // bit-packed maps -> 0/255 bytes
         const size_t words = (size_t)e->H * ((e->W + 31) / 32);
-        const uint32_t* bits = (which == 3 ? e->eb.bits_dil : e->eb.bits_in) + index * words;
-        rc = edge_unpack(bits, e->eb.tmp, e->W, e->H, e->compute_stream);
+        const uint32_t* bits = which == 3 ? e->eb.bits_dil + index * words
+                                          : e->eb.bits_in + index * (size_t)edge_tile_words(e->W, e->H);
+        rc = edge_unpack(bits, e->eb.tmp, e->W, e->H, which == 2, e->compute_stream);
         if (rc) return rc;
         PSD_CUDA(cudaStreamSynchronize(e->compute_stream));
         PSD_CUDA(cudaMemcpy(out, e->eb.tmp, (size_t)e->P, cudaMemcpyDeviceToHost));

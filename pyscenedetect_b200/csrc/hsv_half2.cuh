@@ -33,10 +33,6 @@ namespace psd {
 
 // The LUT is replicated per lane (32 copies of each of the 2 x 256 table values, 64 KB): rows of 128 B in two
 // tables (sdiv | hdiv), lane l reads word l of a row, so any 32 lookups hit 32 distinct banks.
-#ifndef PSD_V7_I2F_D
-#define PSD_V7_I2F_D 0
-#endif
-
 struct LutView7 {
     uint32_t cs;    // addend of the sdiv row address: (0x6400 + V) * 128 + cs = table + V * 128 + lane * 4
     uint32_t ch;    // addend of the hdiv row address: d * 128 + ch
@@ -121,18 +117,7 @@ __device__ __forceinline__ void pair(uint32_t Bh, uint32_t Gh, uint32_t Rh, cons
     const uint32_t eG = heq2m(Vh, Gh);
     const uint32_t hh = bitsel(eR, hR, bitsel(eG, hG, hB));
     // per-lane table products
-#if PSD_V7_I2F_D == 1
-    // d lifted from the integer lanes on the conversion unit (otherwise idle) instead of the fp16 pipe
-    float d0, d1;
-    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.rn.f32.u16 %0, lo; cvt.rn.f32.u16 %1, hi; }"
-        : "=f"(d0), "=f"(d1) : "r"(di));
-#elif PSD_V7_I2F_D == 2
-    float d0;  // one lane on the conversion unit, the other on the fp16 pipe
-    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.u16 %0, lo; }" : "=f"(d0) : "r"(di));
-    const float d1 = __high2float(as_h2(dh));
-#else
     const float d0 = __low2float(as_h2(dh)), d1 = __high2float(as_h2(dh));
-#endif
     const float h0 = __low2float(as_h2(hh)), h1 = __high2float(as_h2(hh));
     const uint32_t aS0 = __dp2a_lo(Vh, 0x00000080u, lut.cs), aS1 = __dp2a_lo(Vh, 0x00008000u, lut.cs);
     const uint32_t aH0 = __dp2a_lo(di, 0x00000080u, lut.ch), aH1 = __dp2a_lo(di, 0x00008000u, lut.ch);

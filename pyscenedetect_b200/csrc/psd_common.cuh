@@ -83,10 +83,10 @@ struct EdgeBuffers {
     uint8_t* vplane;    // [n][P] V of HSV (written by the score pass)
     uint32_t* vhist;    // [n][256]
     int32_t* thresholds;// [n][2] low, high
-    uint32_t* cand;     // [n][H][Wq] Canny candidates (weak or strong pixels), 32 per word
-    uint32_t* bits_in;  // [n][H][Wq] edge pixels: strong pixels after classify, the Canny map after hysteresis
-    uint32_t* bits_row; // [n][H][Wq] row-dilated
-    uint32_t* bits_dil; // [n][H][Wq] dilated edges
+    uint32_t* cand;     // [n][edge_tile_words] Canny candidates (weak or strong pixels), 32 per word, TILE-MAJOR:
+                        // tile (ty, tx) = 32 rows x 64 columns = 64 consecutive words, row r at words 2r, 2r+1
+    uint32_t* bits_in;  // same layout: strong pixels after classify, the Canny map after hysteresis
+    uint32_t* bits_dil; // [n][H][Wq] dilated edges, row-major
     uint32_t* carry_bits; // [H][Wq] dilated edges of the predecessor frame
     uint8_t* tmp;       // [P] scratch for debug taps
     uint8_t* dirty;     // [2][n][tiles] hysteresis: tiles to revisit (double-buffered by round parity)
@@ -94,7 +94,8 @@ struct EdgeBuffers {
 };
 int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
                  psd_frame_sums* sums, cudaStream_t stream);
-int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, cudaStream_t stream);
+int edge_unpack(const uint32_t* bits, uint8_t* out, int W, int H, bool tile_major, cudaStream_t stream);
+int64_t edge_tile_words(int W, int H);   // words per frame of a tile-major bit plane
 
 // ---- perceptual hash (hash_kernels.cu) ----
 struct HashPlan {        // per-engine tables for one (frame size, hash size, lowpass)
