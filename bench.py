@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--detector", default="content",
-                    choices=["content", "content_edges", "adaptive", "threshold", "histogram"],
+                    choices=["content", "content_edges", "adaptive", "threshold", "histogram", "hash"],
                     help="adaptive = BASELINE.json configs[2]: edge component + AdaptiveDetector(window_width=5)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --frames per GPU; strong: --frames in total, split into contiguous time shards")
@@ -147,8 +147,11 @@ def measured_peak_gbs() -> tuple[float, str]:
 # detector configuration per --detector
 # ------------------------------------------------------------------------------------------
 def detector_setup(kind: str):
-    from pyscenedetect_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector, ThresholdDetector
-    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HSV, F_YHIST
+    from pyscenedetect_b200.detectors import (AdaptiveDetector, ContentDetector, HashDetector, HistogramDetector,
+                                              ThresholdDetector)
+    from pyscenedetect_b200.engine import F_BGRSUM, F_EDGES, F_HASH, F_HSV, F_YHIST
+    if kind == "hash":
+        return F_HASH, (lambda: HashDetector()), "HashDetector() defaults: size 8, lowpass 2, threshold 0.35"
     if kind == "adaptive":
         return F_HSV | F_EDGES, (lambda: AdaptiveDetector(window_width=5, weights=ContentDetector.Components(1, 1, 1, 1))), \
             "AdaptiveDetector(window_width=5, weights=(1,1,1,1)) [edge component on]"
@@ -172,6 +175,8 @@ def ref_detector(kind: str):
         return R.RefContentDetector(weights=(1.0, 1.0, 1.0, 1.0))
     if kind == "threshold":
         return R.RefThresholdDetector()
+    if kind == "hash":
+        return R.RefHashDetector()
     return R.RefHistogramDetector(bins=256)
 
 
@@ -359,7 +364,8 @@ def run_ours(args):
         f = compute_downscale_factor(max(W, H))
         sw, sh = (max(1, round(W / f)), max(1, round(H / f))) if f > 1.0 else (W, H)
         max_batch = min(max_batch, 1024)
-    eng = Engine(W, H, features, width=sw, height=sh, device=dev, max_batch=max_batch)
+    eng = Engine(W, H, features, width=sw, height=sh, device=dev, max_batch=max_batch,
+                 **(make_det().engine_kwargs() if args.detector == "hash" else {}))
     weights = (1.0, 1.0, 1.0, 1.0 if args.detector in ("content_edges", "adaptive") else 0.0)
     sums_ptr = None
     n_scan = N
@@ -414,6 +420,11 @@ def run_ours(args):
                 _capi.check(lib.psd_scan_compare(d_val.data_ptr(), N, 27.0, 0, d_flag.data_ptr(), st))
         elif args.detector == "threshold":
             _capi.check(lib.psd_scan_average(sp, N, sw * sh * 3, d_val.data_ptr(), st))
+        elif args.detector == "hash":
+            # the halo frame's hash sits in the slot before stream frame 0, like the histograms
+            hh = eng.device_hash()
+            prev_hash = (hh - _capi.HASH_WORDS * 8) if (world > 1 and rank > 0) else None
+            _capi.check(lib.psd_scan_hash_dist(hh, N, 8, prev_hash, d_val.data_ptr(), st))
         else:
             # the halo frame's histogram sits in the slot before stream frame 0 (psd_b200.h results layout)
             prev_hist = (hp - 256 * 4) if (world > 1 and rank > 0) else None
@@ -471,6 +482,8 @@ def run_ours(args):
         sample = np.empty((n_dl, H, W, 3), dtype=np.uint8)
         _capi.check(lib.psd_memcpy_d2h(dev, sample.ctypes.data, frames_t.data_ptr(), n_dl * fbytes))
         det = ref_detector(args.detector)
+        if args.detector == "hash":
+            det.with_stats = True   # hash_dist is only kept in the stats dict
         t_lo = first
         if rank > 0:
             halo_host = np.empty((H, W, 3), dtype=np.uint8)
@@ -484,6 +497,8 @@ def run_ours(args):
                 oracle_vals.append(float(np.mean(sample[i])))
             elif args.detector == "histogram":
                 oracle_vals.append(None)
+            elif args.detector == "hash":
+                oracle_vals.append(float(det.metrics.get(t_lo + i, {}).get(det.metric_key, float("nan"))))
             else:
                 oracle_vals.append(float(det._frame_score))
         cpu_dt = time.perf_counter() - t_cpu0
@@ -521,7 +536,7 @@ def run_ours(args):
             parity = {"frames": int(n_par), "bit_equal": bool(allp[0][0] > 0.5) if args.detector != "histogram" else None,
                       "within_1e-4": bool(allp[0][0] > 0.5), "max_abs_err": float(max(float(x[1]) for x in allp)),
                       "cuts_equal": (bool(allp[0][2] > 0.5) if cuts_ok is not None else None),
-                      "metric": {"threshold": "average_rgb", "histogram": "hist_diff"}.get(args.detector, "content_val"),
+                      "metric": {"threshold": "average_rgb", "histogram": "hist_diff", "hash": "hash_dist"}.get(args.detector, "content_val"),
                       "oracle": "oracle.ref_detectors on the same frames (downloaded from HBM after the timed steps)"}
             if world > 1:
                 parity["shard_boundaries_checked"] = world - 1
@@ -551,7 +566,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "psd_score_ws_kernel (fused TMA time-marching pass)",
+                "bound": "hbm", "kernel": ("psd_hash_rows_kernel + psd_hash_finish_kernel (gray, INTER_AREA, DCT, median)"
+                                           if args.detector == "hash" else "psd_score_ws_kernel (fused TMA time-marching pass)"),
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": fbytes,

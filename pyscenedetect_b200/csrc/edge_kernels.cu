@@ -274,37 +274,62 @@ __device__ int g_hs_launch;
 
 __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
-                                                            uint8_t* __restrict__ dirty /* [2][n_tiles] */,
-                                                            int32_t* __restrict__ flags /* [3] */, int W, int H,
-                                                            int Wq, int tiles_x, int tiles_y, int64_t n_tiles) {
+                                                            uint8_t* __restrict__ dirty /* [n_tiles] */,
+                                                            int32_t* __restrict__ worklist /* [n_tiles] */,
+                                                            int32_t* __restrict__ counts /* [3] */,
+                                                            int tiles_x, int tiles_y, int64_t n_tiles) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t per_frame_tiles = (int64_t)tiles_x * tiles_y;
-    // a warp owns a contiguous run of tiles: their dirty bytes are read 32 at a time, one per lane
+    // phase A of a round: a warp scans the dirty bytes of a contiguous run of tiles, 32 at a time, one per lane
     const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
     const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles);
 
     for (int round = 0; round < 100000; ++round) {
-        uint8_t* dcur = dirty + (int64_t)(round & 1) * n_tiles;
-        uint8_t* dnext = dirty + (int64_t)((round + 1) & 1) * n_tiles;
-        if (blockIdx.x == 0 && threadIdx.x == 0) flags[(round + 1) % 3] = 0;
-        bool warp_changed = false;
+        // ---- A: compact the dirty tiles into the work list (dirty tiles cluster - whole frames, image regions -
+        //         so visiting them straight from the owner's run leaves most warps idle: round times followed
+        //         the busiest warp, profiles/r02i_edge_ab_summary.txt) ----
+        int32_t* count = counts + round % 3;
         for (int64_t base = t_begin; base < t_end; base += 32) {
-            uint32_t todo;  // bit l: tile base + l needs a visit this round
-            {
-                const int64_t mine = base + lane;
-                bool need = mine < t_end;
-                if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
-                    need = dcur[mine] != 0;
-                    if (need) dcur[mine] = 0;
-                }
-                todo = __ballot_sync(0xFFFFFFFFu, need);
+            const int64_t mine = base + lane;
+            bool need = mine < t_end;
+            if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
+                need = dirty[mine] != 0;
+                if (need) dirty[mine] = 0;
             }
-            while (todo) {
-                const int64_t t = base + __ffs(todo) - 1;
-                todo &= todo - 1;
+            const uint32_t todo = __ballot_sync(0xFFFFFFFFu, need);
+            if (todo == 0u) continue;
+            int off = 0;
+            if (lane == 0) off = atomicAdd(count, __popc(todo));
+            off = __shfl_sync(0xFFFFFFFFu, off, 0);
+            if (need) worklist[off + __popc(todo & ((1u << lane) - 1u))] = (int32_t)mine;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) counts[(round + 1) % 3] = 0;
+        __threadfence();
+        grid.sync();
+        const int64_t n_work = *(volatile int32_t*)count;
+        if (n_work == 0) {
+#if PSD_HYST_STATS
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const int l = atomicAdd(&g_hs_launch, 1);
+                if (l == 4 || l == 9) {   // a warm launch
+                    printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round, (long long)n_tiles, (int)gridDim.x);
+                    for (int r = 0; r < round && r < 512; ++r)
+                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  +%llu ns\n", r,
+                               g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
+                               r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
+                }
+                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
+            }
+#endif
+            break;
+        }
+        // ---- B: every warp takes every n_warps-th entry of the list ----
+        {
+            for (int64_t wi = warp0; wi < n_work; wi += n_warps) {
+                const int64_t t = worklist[wi];
                 HS_COUNT(g_hs_visit, round);
                 const int64_t f = t / per_frame_tiles;
                 const int tt = (int)(t - f * per_frame_tiles);
@@ -363,18 +388,16 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 const bool changed = e != e_in;
                 if (changed) reinterpret_cast<uint2*>(Et)[lane] = make_uint2((uint32_t)e, (uint32_t)(e >> 32));
                 if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
-                    warp_changed = true;
                     HS_COUNT(g_hs_change, round);
                     // the ring of the 8 neighbours may have changed: they look again next round
                     if (lane < 9 && lane != 4) {
                         const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
                         if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x)
-                            dnext[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
+                            dirty[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
                     }
                 }
             }
         }
-        if (warp_changed && lane == 0) atomicOr(&flags[round % 3], 1);
         __threadfence();
         grid.sync();
 #if PSD_HYST_STATS
@@ -384,22 +407,6 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
             g_hs_time[round] = now;
         }
 #endif
-        if (*(volatile int32_t*)&flags[round % 3] == 0) {
-#if PSD_HYST_STATS
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                const int l = atomicAdd(&g_hs_launch, 1);
-                if (l == 4 || l == 9) {   // a warm launch
-                    printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round + 1, (long long)n_tiles, (int)gridDim.x);
-                    for (int r = 0; r <= round && r < 512; ++r)
-                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  +%llu ns\n", r,
-                               g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
-                               r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
-                }
-                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
-            }
-#endif
-            break;
-        }
     }
 }
 
@@ -447,7 +454,11 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_any_bits_kernel(const uin
 
 // the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a band of kDilBand rows and
 // marches down it with the last 2 R + 1 horizontally dilated rows in registers (the row loop is unrolled
-// 2 R + 1 times so the ring slots are register names): 3 loads per output word.
+// 2 R + 1 times so the ring slots are register names).  Consecutive lanes own consecutive word columns of the
+// same band, so the left / right neighbour words come from the neighbouring LANES (two shuffles) and only the
+// first and last lane of a warp load theirs: one load per output word (a tile-major load touches 16 sectors
+// per warp, three of them per row cost more than the row-major version of this kernel did).  Every lane runs
+// the same kDilBand + 2 R steps; rows and lanes outside the image are predicates, not branches.
 constexpr int kDilBand = 32;
 
 template <int R>
@@ -456,33 +467,47 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_
                                                                    int tiles_x, int64_t tile_words_per_frame,
                                                                    int bands, int64_t n_threads,
                                                                    uint32_t last_word_mask) {
-    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (gid >= n_threads) return;
+    const int64_t gid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool active = gid0 < n_threads;
+    const int64_t gid = active ? gid0 : n_threads - 1;   // idle lanes shadow the last thread and store nothing
+    const int lane = threadIdx.x & 31;
     const int wq = (int)(gid % Wq);
     const int band = (int)((gid / Wq) % bands);
     const int64_t f = gid / ((int64_t)Wq * bands);
     const uint32_t* src = in + f * tile_words_per_frame;
     uint32_t* dst = out + f * (int64_t)H * Wq + wq;
     const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;   // columns >= W stay 0
+    const bool has_prv = wq > 0, has_nxt = wq + 1 < Wq;
+    const bool load_prv = has_prv && lane == 0, load_nxt = has_nxt && lane == 31;
     auto hdil = [&](int y) -> uint32_t {
-        if (y < 0 || y >= H) return 0u;
-        return hdil_word<R>(src, tiles_x, Wq, y, wq, R, keep);
+        const bool row_in = y >= 0 && y < H;
+        const uint32_t cur = row_in ? tiled_word(src, tiles_x, y, wq) : 0u;
+        uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, cur, 1), nxt = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+        if (load_prv) prv = row_in ? tiled_word(src, tiles_x, y, wq - 1) : 0u;
+        if (load_nxt) nxt = row_in ? tiled_word(src, tiles_x, y, wq + 1) : 0u;
+        if (!has_prv) prv = 0u;
+        if (!has_nxt) nxt = 0u;
+        uint32_t o = cur;
+#pragma unroll
+        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+        return o & keep;
     };
     constexpr int K = 2 * R + 1;
     uint32_t ring[K];
-    const int y0 = band * kDilBand, y1 = min(y0 + kDilBand, H);
+    const int y0 = band * kDilBand;
 #pragma unroll
     for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
 #pragma unroll 1
-    for (int y = y0; y < y1; y += K) {
+    for (int yo = 0; yo < kDilBand; yo += K) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            if (y + j < y1) {
-                ring[(K - 1 + j) % K] = hdil(y + j + R);
+            if (yo + j < kDilBand) {
+                const int y = y0 + yo + j;
+                ring[(K - 1 + j) % K] = hdil(y + R);
                 uint32_t o = 0;
 #pragma unroll
                 for (int i = 0; i < K; ++i) o |= ring[i];
-                dst[(int64_t)(y + j) * Wq] = o;
+                if (active && y < H) dst[(int64_t)y * Wq] = o;
             }
         }
     }
@@ -560,7 +585,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         // (bytes of the planes that no strip writes - beyond the last strip, below the last row - were zeroed
         // when the planes were allocated and nothing ever sets them)
         const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
-        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles0, stream));
+        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)n_tiles0, stream));
         if ((W & 7) == 0)
             psd_canny_classify_pairs_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
@@ -588,9 +613,9 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         uint32_t* e_ptr = b.bits_in;
         const uint32_t* c_ptr = b.cand;
         uint8_t* d_ptr = b.dirty;
+        int32_t* l_ptr = b.worklist;
         int32_t* f_ptr = b.hyst_flags;
-        int w_ = W, h_ = H, wq_ = Wq;
-        void* args[] = {&e_ptr, &c_ptr, &d_ptr, &f_ptr, &w_, &h_, &wq_, &tiles_x, &tiles_y, &n_tiles};
+        void* args[] = {&e_ptr, &c_ptr, &d_ptr, &l_ptr, &f_ptr, &tiles_x, &tiles_y, &n_tiles};
         PSD_CUDA(cudaLaunchCooperativeKernel((const void*)psd_hyst_bits_kernel, dim3(grid), dim3(256), args, 0, stream));
     }
     count_launch(3);
