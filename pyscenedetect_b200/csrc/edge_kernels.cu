@@ -23,6 +23,13 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef PSD_CLASSIFY_SWP
+#define PSD_CLASSIFY_SWP 0   // 1: load the row window one row ahead into registers (A/B)
+#endif
+#ifndef PSD_CLASSIFY_BLOCK
+#define PSD_CLASSIFY_BLOCK 256
+#define PSD_CLASSIFY_CTAS 2
+#endif
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
 #endif
@@ -90,7 +97,7 @@ constexpr int kBandRows = 32;   // == kHystTileH: a band of the classify kernel 
 constexpr int kTileWords = 64;  // 32 rows x 2 words
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
+__global__ void __launch_bounds__(PSD_CLASSIFY_BLOCK, PSD_CLASSIFY_CTAS) psd_canny_classify_pairs_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
     uint32_t* __restrict__ cand_bits, uint8_t* __restrict__ tile_dirty, int W, int H, int Wq, int strips,
     int bands, int64_t n_threads) {
@@ -140,9 +147,18 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
     };
     // Row yy+1 arrives: magnitudes (and, if asked, sectors) of row yy from the sums of rows yy-1 (`so`,
     // replaced by row yy+1 on the way out), yy (`sm`) and yy+1.
+#if PSD_CLASSIFY_SWP
+    uint32_t wn[4];   // the window of the next row to arrive, loaded one row early
+#endif
     auto advance = [&](int yy, cp::Sums& so, const cp::Sums& sm, cp::Mags& r, bool want_sectors) {
         uint32_t w[4];
+#if PSD_CLASSIFY_SWP
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = wn[i];
+        load_window(yy + 2, wn);
+#else
         load_window(yy + 1, w);
+#endif
         // the first touch of a row goes to L2 / HBM and four warps per scheduler cannot hide that: pull the line
         // of the row two further down into L1 now (no register, no dependency; +4 % on the edge path)
         if (yy + 3 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (int64_t)(yy + 3) * W + x0));
@@ -217,6 +233,9 @@ __global__ void __launch_bounds__(256, 2) psd_canny_classify_pairs_kernel(
         cp::row_sums(w, sa);
         load_window(yb - 1, w);
         cp::row_sums(w, sb);
+#if PSD_CLASSIFY_SWP
+        load_window(yb, wn);
+#endif
         advance(yb - 1, sa, sb, r0, false);   // sa: yb-2 -> yb
         advance(yb, sb, sa, r1, true);        // sb: yb-1 -> yb+1
     }
@@ -581,16 +600,17 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     {
         const int strips = (W + 7) / 8, bands = (H + kBandRows - 1) / kBandRows;
         const int64_t n_threads = (int64_t)strips * bands * n;
-        const unsigned blocks = (unsigned)((n_threads + 255) / 256);
+        const unsigned cblock = PSD_CLASSIFY_BLOCK;
+        const unsigned blocks = (unsigned)((n_threads + cblock - 1) / cblock);
         // (bytes of the planes that no strip writes - beyond the last strip, below the last row - were zeroed
         // when the planes were allocated and nothing ever sets them)
         const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
         PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)n_tiles0, stream));
         if ((W & 7) == 0)
-            psd_canny_classify_pairs_kernel<true><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
+            psd_canny_classify_pairs_kernel<true><<<blocks, cblock, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
         else
-            psd_canny_classify_pairs_kernel<false><<<blocks, 256, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
+            psd_canny_classify_pairs_kernel<false><<<blocks, cblock, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                                b.dirty, W, H, Wq, strips, bands, n_threads);
         PSD_CHECK_LAUNCH();
     }
