@@ -24,11 +24,14 @@
 namespace cg = cooperative_groups;
 
 #ifndef PSD_CLASSIFY_SWP
-#define PSD_CLASSIFY_SWP 0   // 1: load the row window one row ahead into registers (A/B)
+#define PSD_CLASSIFY_SWP 1   // load the row window one row ahead into registers
 #endif
 #ifndef PSD_CLASSIFY_BLOCK
-#define PSD_CLASSIFY_BLOCK 256
-#define PSD_CLASSIFY_CTAS 2
+#define PSD_CLASSIFY_BLOCK 128   // 128 x 3: 163 registers, no spills (256 x 2 caps at 128 and spills ~50 words)
+#define PSD_CLASSIFY_CTAS 3
+#endif
+#ifndef PSD_DILATE_CTAS
+#define PSD_DILATE_CTAS 3
 #endif
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
@@ -291,13 +294,14 @@ __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
+__global__ void __launch_bounds__(256, 4) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
                                                             uint8_t* __restrict__ dirty /* [n_tiles] */,
                                                             int32_t* __restrict__ worklist /* [n_tiles] */,
                                                             int32_t* __restrict__ counts /* [3] */,
                                                             int tiles_x, int tiles_y, int64_t n_tiles) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ int s_cnt[9];   // phase A: dirty tiles per warp -> exclusive prefix; [8] = the CTA's base in the list
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -311,7 +315,26 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
         //         so visiting them straight from the owner's run leaves most warps idle: round times followed
         //         the busiest warp, profiles/r02i_edge_ab_summary.txt) ----
         int32_t* count = counts + round % 3;
+        // one atomic per CTA and round on the list length (one per 32 tiles serialised ~16 k same-address
+        // atomics per round at L2 and doubled the kernel's time): count, reserve, then write
+        int n_mine = 0;
         for (int64_t base = t_begin; base < t_end; base += 32) {
+            const int64_t mine = base + lane;
+            const bool need = mine < t_end && dirty[mine] != 0;
+            n_mine += __popc(__ballot_sync(0xFFFFFFFFu, need));
+        }
+        if (lane == 0) s_cnt[threadIdx.x >> 5] = n_mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_cnt[8] = tot ? atomicAdd(count, tot) : 0;
+        }
+        __syncthreads();
+        int off = s_cnt[8] + s_cnt[threadIdx.x >> 5];
+        __syncthreads();   // s_cnt is rewritten next round
+        for (int64_t base = t_begin; base < t_end && n_mine; base += 32) {
             const int64_t mine = base + lane;
             bool need = mine < t_end;
             if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
@@ -319,11 +342,8 @@ __global__ void __launch_bounds__(256) psd_hyst_bits_kernel(uint32_t* __restrict
                 if (need) dirty[mine] = 0;
             }
             const uint32_t todo = __ballot_sync(0xFFFFFFFFu, need);
-            if (todo == 0u) continue;
-            int off = 0;
-            if (lane == 0) off = atomicAdd(count, __popc(todo));
-            off = __shfl_sync(0xFFFFFFFFu, off, 0);
             if (need) worklist[off + __popc(todo & ((1u << lane) - 1u))] = (int32_t)mine;
+            off += __popc(todo);
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) counts[(round + 1) % 3] = 0;
         __threadfence();
@@ -471,75 +491,100 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_any_bits_kernel(const uin
     dil[f * per_frame + i] = o;
 }
 
-// the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a band of kDilBand rows and
-// marches down it with the last 2 R + 1 horizontally dilated rows in registers (the row loop is unrolled
-// 2 R + 1 times so the ring slots are register names).  Consecutive lanes own consecutive word columns of the
-// same band, so the left / right neighbour words come from the neighbouring LANES (two shuffles) and only the
-// first and last lane of a warp load theirs: one load per output word (a tile-major load touches 16 sectors
-// per warp, three of them per row cost more than the row-major version of this kernel did).  Every lane runs
-// the same kDilBand + 2 R steps; rows and lanes outside the image are predicates, not branches.
+// the usual kernel sizes (k = 2 R + 1 <= 17), dilation AND the SAD in one pass.  A thread owns one word column of
+// a band of kDilBand rows and walks a chunk of kDilChunk consecutive frames; per frame it marches down the band
+// with the last 2 R + 1 horizontally dilated rows in registers (the row loop is fully unrolled, so the ring slots
+// and the 32 words of the previous frame's dilated column are register names), stores the dilated word and
+// counts the bits that differ from the previous frame's word - which it still holds.  The first frame of a chunk
+// gets its predecessor by dilating it once more (1 / kDilChunk extra work) or, for the first frame of the batch,
+// from the carry plane.  Consecutive lanes own consecutive word columns of the same band, so the left / right
+// neighbour words come from the neighbouring LANES (two shuffles) and only the first and last lane of a warp
+// load theirs: one load per output word.  Every lane runs the same steps; rows, frames and lanes outside the
+// work are predicates, not branches.
 constexpr int kDilBand = 32;
+constexpr int kDilChunk = 8;
 
 template <int R>
-__global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_t* __restrict__ in,
-                                                                   uint32_t* __restrict__ out, int H, int Wq,
-                                                                   int tiles_x, int64_t tile_words_per_frame,
-                                                                   int bands, int64_t n_threads,
-                                                                   uint32_t last_word_mask) {
+__global__ void __launch_bounds__(256, PSD_DILATE_CTAS) psd_edge_dilate_sad_kernel(const uint32_t* __restrict__ in,
+                                                                  uint32_t* __restrict__ out,
+                                                                  const uint32_t* __restrict__ carry, int n, int H,
+                                                                  int Wq, int tiles_x, int64_t tile_words_per_frame,
+                                                                  int bands, int64_t n_threads,
+                                                                  uint32_t last_word_mask, int have_prev,
+                                                                  psd_frame_sums* __restrict__ sums) {
     const int64_t gid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = gid0 < n_threads;
-    const int64_t gid = active ? gid0 : n_threads - 1;   // idle lanes shadow the last thread and store nothing
+    const int64_t gid = active ? gid0 : n_threads - 1;   // idle lanes shadow the last thread and contribute nothing
     const int lane = threadIdx.x & 31;
     const int wq = (int)(gid % Wq);
     const int band = (int)((gid / Wq) % bands);
-    const int64_t f = gid / ((int64_t)Wq * bands);
-    const uint32_t* src = in + f * tile_words_per_frame;
-    uint32_t* dst = out + f * (int64_t)H * Wq + wq;
+    const int chunk = (int)(gid / ((int64_t)Wq * bands));
     const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;   // columns >= W stay 0
     const bool has_prv = wq > 0, has_nxt = wq + 1 < Wq;
     const bool load_prv = has_prv && lane == 0, load_nxt = has_nxt && lane == 31;
-    auto hdil = [&](int y) -> uint32_t {
-        const bool row_in = y >= 0 && y < H;
-        const uint32_t cur = row_in ? tiled_word(src, tiles_x, y, wq) : 0u;
-        uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, cur, 1), nxt = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
-        if (load_prv) prv = row_in ? tiled_word(src, tiles_x, y, wq - 1) : 0u;
-        if (load_nxt) nxt = row_in ? tiled_word(src, tiles_x, y, wq + 1) : 0u;
-        if (!has_prv) prv = 0u;
-        if (!has_nxt) nxt = 0u;
-        uint32_t o = cur;
-#pragma unroll
-        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
-        return o & keep;
-    };
-    constexpr int K = 2 * R + 1;
-    uint32_t ring[K];
     const int y0 = band * kDilBand;
-#pragma unroll
-    for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
+    const int64_t per_frame = (int64_t)H * Wq;
+    constexpr int K = 2 * R + 1;
+    uint32_t prev[kDilBand];   // the previous frame's dilated words of this column
+    const int f_first = chunk * kDilChunk;
+    // lanes of one warp can sit in two chunks (a warp straddles the end of a frame's thread range)
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, chunk);
+    const bool leader = lane == __ffs(peers) - 1;
+
+    // step -1 rebuilds the predecessor of the chunk's first frame (or takes it from the carry plane)
 #pragma unroll 1
-    for (int yo = 0; yo < kDilBand; yo += K) {
+    for (int step = -1; step < kDilChunk; ++step) {
+        const int f = f_first + step;
+        const bool frame_in = f >= 0 && f < n;
+        const bool from_carry = f < 0;                         // only chunk 0, step -1
+        const bool counted = step >= 0 && frame_in && active && (f > 0 || have_prev);
+        const uint32_t* src = in + (int64_t)(frame_in ? f : 0) * tile_words_per_frame;
+        auto hdil = [&](int y) -> uint32_t {
+            const bool row_in = frame_in && y >= 0 && y < H;
+            const uint32_t cur = row_in ? tiled_word(src, tiles_x, y, wq) : 0u;
+            uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, cur, 1), nxt = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+            if (load_prv) prv = row_in ? tiled_word(src, tiles_x, y, wq - 1) : 0u;
+            if (load_nxt) nxt = row_in ? tiled_word(src, tiles_x, y, wq + 1) : 0u;
+            if (!has_prv) prv = 0u;
+            if (!has_nxt) nxt = 0u;
+            uint32_t o = cur;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (yo + j < kDilBand) {
-                const int y = y0 + yo + j;
-                ring[(K - 1 + j) % K] = hdil(y + R);
-                uint32_t o = 0;
+            for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+            return o & keep;
+        };
+        uint32_t ring[K];
 #pragma unroll
-                for (int i = 0; i < K; ++i) o |= ring[i];
-                if (active && y < H) dst[(int64_t)y * Wq] = o;
-            }
+        for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kDilBand; ++j) {
+            const int y = y0 + j;
+            ring[(K - 1 + j) % K] = hdil(y + R);
+            uint32_t o = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) o |= ring[i];
+            if (from_carry) o = (have_prev && y < H) ? carry[(int64_t)y * Wq + wq] : 0u;
+            if (counted && y < H) cnt += __popc(o ^ prev[j]);
+            prev[j] = o;
+            if (step >= 0 && frame_in && active && y < H) out[f * per_frame + (int64_t)y * Wq + wq] = o;
         }
+        cnt = __reduce_add_sync(peers, cnt);
+        if (leader && cnt && step >= 0 && frame_in)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&sums[f].sad_edges), 255ull * cnt);
     }
 }
 
 template <int R>
-static void launch_dilate(const uint32_t* in, uint32_t* out, int n, int H, int Wq, uint32_t mask, cudaStream_t stream) {
+static void launch_dilate_sad(const EdgeBuffers& b, int n, int H, int Wq, uint32_t mask, bool have_prev,
+                              psd_frame_sums* sums, cudaStream_t stream) {
     const int bands = (H + kDilBand - 1) / kDilBand;
+    const int chunks = (n + kDilChunk - 1) / kDilChunk;
     const int tiles_x = (Wq + 1) / 2;
     const int64_t tile_words = (int64_t)tiles_x * ((H + kHystTileH - 1) / kHystTileH) * kTileWords;
-    const int64_t n_threads = (int64_t)Wq * bands * n;
-    psd_edge_dilate_bits_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(
-        in, out, H, Wq, tiles_x, tile_words, bands, n_threads, mask);
+    const int64_t n_threads = (int64_t)Wq * bands * chunks;
+    psd_edge_dilate_sad_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(
+        b.bits_in, b.bits_dil, b.carry_bits, n, H, Wq, tiles_x, tile_words, bands, n_threads, mask, have_prev ? 1 : 0,
+        sums);
 }
 
 __global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* __restrict__ dil,
@@ -642,25 +687,26 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     const int r = ksize / 2;
     const uint32_t last_mask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu;
     switch (r) {
-        case 1: launch_dilate<1>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 2: launch_dilate<2>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 3: launch_dilate<3>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 4: launch_dilate<4>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 5: launch_dilate<5>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 6: launch_dilate<6>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 7: launch_dilate<7>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        case 8: launch_dilate<8>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
-        default: {   // any other kernel size
+        case 1: launch_dilate_sad<1>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 2: launch_dilate_sad<2>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 3: launch_dilate_sad<3>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 4: launch_dilate_sad<4>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 5: launch_dilate_sad<5>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 6: launch_dilate_sad<6>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 7: launch_dilate_sad<7>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        case 8: launch_dilate_sad<8>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
+        default: {   // any other kernel size: one thread per output word, then the SAD
             dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
             psd_edge_dilate_any_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_in, b.bits_dil, H, Wq, (Wq + 1) / 2,
                                                                      edge_tile_words(W, H), r, last_mask);
+            PSD_CHECK_LAUNCH();
+            dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
+            psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
+            count_launch(1);
         }
     }
     PSD_CHECK_LAUNCH();
-    dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
-    psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
-    PSD_CHECK_LAUNCH();
-    count_launch(2);
+    count_launch(1);
     PSD_CUDA(cudaMemcpyAsync(b.carry_bits, b.bits_dil + (int64_t)(n - 1) * per_frame,
                              (size_t)per_frame * 4, cudaMemcpyDeviceToDevice, stream));
     return PSD_OK;

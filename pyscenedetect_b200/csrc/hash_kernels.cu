@@ -18,33 +18,75 @@
 
 namespace psd {
 
-__device__ __forceinline__ uint32_t gray_px(const uint8_t* p) {
-    return ((uint32_t)p[0] * 3735u + (uint32_t)p[1] * 19235u + (uint32_t)p[2] * 9798u + 16384u) >> 15;
+__device__ __forceinline__ uint32_t gray_bgr(uint32_t b, uint32_t g, uint32_t r) {
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
 }
 
-// one thread per (frame, source row, destination column): the horizontal pass
+// The horizontal pass.  A CTA takes a block of consecutive source rows of one frame (256 / n of them):
+//   1. all threads pull the block - it is contiguous in memory - 16 pixels (three 16-byte loads) at a time,
+//      convert to gray and park the gray bytes in shared memory (row pitch W rounded up + 4: two rows of a
+//      1920-wide frame would otherwise sit in the same banks);
+//   2. thread (row, destination column) walks its taps in shared memory: the integer block sum if both scale
+//      factors are integers, else OpenCV's float32 `buf += S * alpha` in source order (separate multiply and
+//      add: the order and the roundings decide the last bit, so this chain stays sequential).
+// (The first version had one thread per (row, column) read its 3 x 120 bytes straight from global memory, 32
+// lanes 360 bytes apart: 0.085 of the HBM roofline, profiles/r02i_edge_ab_summary.txt.)
 __global__ void __launch_bounds__(256) psd_hash_rows_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride,
-                                                            int W, int H, int n, int fast,
+                                                            int W, int H, int n, int rows_per_cta, int pitch, int fast,
                                                             const int32_t* __restrict__ xstart,
                                                             const int32_t* __restrict__ xsi,
                                                             const float* __restrict__ xalpha,
-                                                            float* __restrict__ rowbuf, int64_t total) {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    const int dx = (int)(g % n);
-    const int sy = (int)((g / n) % H);
-    const int64_t f = g / ((int64_t)n * H);
-    const uint8_t* row = frames + f * frame_stride + (int64_t)sy * W * 3;
+                                                            float* __restrict__ rowbuf) {
+    extern __shared__ __align__(16) uint8_t sgray[];   // [rows_per_cta][pitch]
+    const int tid = threadIdx.x;
+    const int64_t f = blockIdx.y;
+    const int sy0 = blockIdx.x * rows_per_cta;
+    const int rows = min(rows_per_cta, H - sy0);
+    const uint8_t* blk = frames + f * frame_stride + (int64_t)sy0 * W * 3;
+    const int n_px = rows * W;
+    // ---- 1. gray bytes of the block ----
+    if ((W & 15) == 0 && ((reinterpret_cast<uintptr_t>(blk) & 15) == 0)) {
+        for (int q = tid * 16; q < n_px; q += 256 * 16) {   // a group of 16 pixels never straddles a row
+            const uint4* p = reinterpret_cast<const uint4*>(blk + (int64_t)q * 3);
+            const uint4 a = p[0], b = p[1], c = p[2];
+            const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            const int r = q / W, x = q - r * W;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sgray + r * pitch + x);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {   // 4 pixels = 12 bytes = words 3 g4 .. 3 g4 + 2
+                const uint32_t w0 = w[3 * g4], w1 = w[3 * g4 + 1], w2 = w[3 * g4 + 2];
+                const uint32_t g0 = gray_bgr(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+                const uint32_t g1 = gray_bgr(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+                const uint32_t g2 = gray_bgr((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+                const uint32_t g3 = gray_bgr((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+                dst[g4] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+            }
+        }
+    } else {
+        for (int q = tid; q < n_px; q += 256) {
+            const int r = q / W, x = q - r * W;
+            const uint8_t* p = blk + (int64_t)q * 3;
+            sgray[r * pitch + x] = (uint8_t)gray_bgr(p[0], p[1], p[2]);
+        }
+    }
+    __syncthreads();
+    // ---- 2. one thread per (row, destination column) ----
+    const int r = tid / n, dx = tid - r * n;
+    if (r >= rows) return;
+    const uint8_t* srow = sgray + r * pitch;
+    float* out = rowbuf + (f * H + sy0 + r) * (int64_t)n + dx;
     if (fast) {  // integer scale: exact integer sum of the block's columns
         const int sxw = W / n;
         uint32_t s = 0;
-        for (int x = dx * sxw; x < (dx + 1) * sxw; ++x) s += gray_px(row + 3 * x);
-        rowbuf[g] = __uint_as_float(s);
+        for (int x = dx * sxw; x < (dx + 1) * sxw; ++x) s += srow[x];
+        *out = __uint_as_float(s);
     } else {
         float buf = 0.0f;
-        for (int k = xstart[dx]; k < xstart[dx + 1]; ++k)
-            buf = __fadd_rn(buf, __fmul_rn((float)gray_px(row + 3 * xsi[k]), xalpha[k]));
-        rowbuf[g] = buf;
+        const int k1 = xstart[dx + 1];
+#pragma unroll 4
+        for (int k = xstart[dx]; k < k1; ++k)
+            buf = __fadd_rn(buf, __fmul_rn((float)srow[xsi[k]], xalpha[k]));
+        *out = buf;
     }
 }
 
@@ -267,9 +309,15 @@ void hash_plan_destroy(HashPlan* p) {
 
 int launch_hash(const HashPlan& p, const uint8_t* frames, int64_t frame_stride, int n_frames, int W, int H,
                 uint64_t* hashes, cudaStream_t stream) {
-    const int64_t total = (int64_t)n_frames * H * p.n;
-    psd_hash_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(frames, frame_stride, W, H, p.n, p.fast,
-                                                                             p.xstart, p.xsi, p.xalpha, p.rowbuf, total);
+    // rows kernel: 256 / n source rows per CTA, their gray bytes in shared memory
+    const int rows_per_cta = 256 / p.n;
+    const int pitch = ((W + 3) & ~3) + 4;
+    const size_t smem_rows = (size_t)rows_per_cta * pitch;
+    PSD_REQUIRE(smem_rows <= 200 * 1024, "frame too wide for the hash rows kernel (%d columns)", W);
+    PSD_CUDA(cudaFuncSetAttribute(psd_hash_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    dim3 rgrid((unsigned)((H + rows_per_cta - 1) / rows_per_cta), (unsigned)n_frames);
+    psd_hash_rows_kernel<<<rgrid, 256, smem_rows, stream>>>(frames, frame_stride, W, H, p.n, rows_per_cta, pitch, p.fast,
+                                                            p.xstart, p.xsi, p.xalpha, p.rowbuf);
     PSD_CHECK_LAUNCH();
     FoldPlan fp{};
     fp.levels = p.levels;
