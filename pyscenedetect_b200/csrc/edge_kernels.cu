@@ -30,8 +30,8 @@ namespace cg = cooperative_groups;
 #define PSD_CLASSIFY_BLOCK 128   // 128 x 3: 163 registers, no spills (256 x 2 caps at 128 and spills ~50 words)
 #define PSD_CLASSIFY_CTAS 3
 #endif
-#ifndef PSD_DILATE_CTAS
-#define PSD_DILATE_CTAS 3
+#ifndef PSD_HYST_CTAS
+#define PSD_HYST_CTAS 3   // 85 registers: room for the next tile's loads
 #endif
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
@@ -286,6 +286,42 @@ __device__ __forceinline__ unsigned long long run_fill(unsigned long long t, uns
     return up | dn;
 }
 
+// what a warp pulls for one tile: lane r holds row r of C and E, the E words left and right of the row, and
+// (lanes 0 and 31) the ring row above / below with its two corner words.  Tile-major planes: the tile is 64
+// consecutive words, one 256-byte request per plane; rows beyond the image and the second word of a last odd
+// column hold 0 in both planes.
+struct TileLoad {
+    int64_t t;
+    uint2 cw, ew;
+    uint32_t e_l, e_r, g_lo, g_hi, g_l, g_r;
+};
+
+__device__ __forceinline__ TileLoad load_tile(const uint32_t* __restrict__ edge_bits, const uint32_t* __restrict__ cand_bits,
+                                              int64_t t, int64_t per_frame_tiles, int tiles_x, int tiles_y, int lane) {
+    TileLoad d;
+    d.t = t;
+    const int tt = (int)(t % per_frame_tiles);
+    const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+    const uint32_t* Et = edge_bits + t * kTileWords;
+    const uint32_t* Ct = cand_bits + t * kTileWords;
+    const bool has_left = tx > 0, has_right = tx + 1 < tiles_x;
+    d.cw = reinterpret_cast<const uint2*>(Ct)[lane];
+    d.ew = reinterpret_cast<const uint2*>(Et)[lane];
+    d.e_l = has_left ? Et[-kTileWords + 2 * lane + 1] : 0u;   // word 1 of the left tile
+    d.e_r = has_right ? Et[kTileWords + 2 * lane] : 0u;       // word 0 of the right tile
+    // ring rows: lane 0 fetches row 31 of the tile above, lane 31 row 0 of the tile below
+    const bool ring_in = (lane == 0 && ty > 0) || (lane == 31 && ty + 1 < tiles_y);
+    d.g_lo = d.g_hi = d.g_l = d.g_r = 0u;
+    if (ring_in) {
+        const uint32_t* pe = (lane == 0) ? Et - (int64_t)tiles_x * kTileWords + 62 : Et + (int64_t)tiles_x * kTileWords;
+        d.g_lo = pe[0];
+        d.g_hi = pe[1];
+        if (has_left) d.g_l = pe[-kTileWords + 1];
+        if (has_right) d.g_r = pe[kTileWords];
+    }
+    return d;
+}
+
 #if PSD_HYST_STATS   // alt build for tools/gpu_*.sh: per-round tile counts and times of the first launches
 __device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512];
 __device__ int g_hs_launch;
@@ -294,7 +330,7 @@ __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(256, 4) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
+__global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
                                                             uint8_t* __restrict__ dirty /* [n_tiles] */,
                                                             int32_t* __restrict__ worklist /* [n_tiles] */,
@@ -365,36 +401,25 @@ __global__ void __launch_bounds__(256, 4) psd_hyst_bits_kernel(uint32_t* __restr
 #endif
             break;
         }
-        // ---- B: every warp takes every n_warps-th entry of the list ----
+        // ---- B: every warp takes every n_warps-th entry of the list.  A warp works through its tiles one after
+        //         the other and a tile starts with two dependent trips to L2 (list entry, then the tile and its
+        //         ring): the loads of the NEXT tile are issued before the fill loop of the current one. ----
         {
-            for (int64_t wi = warp0; wi < n_work; wi += n_warps) {
-                const int64_t t = worklist[wi];
+            TileLoad cur, nxt;
+            int64_t wi = warp0;
+            if (wi < n_work) cur = load_tile(edge_bits, cand_bits, worklist[wi], per_frame_tiles, tiles_x, tiles_y, lane);
+            for (; wi < n_work; wi += n_warps, cur = nxt) {
+                if (wi + n_warps < n_work)
+                    nxt = load_tile(edge_bits, cand_bits, worklist[wi + n_warps], per_frame_tiles, tiles_x, tiles_y, lane);
+                const int64_t t = cur.t;
                 HS_COUNT(g_hs_visit, round);
                 const int64_t f = t / per_frame_tiles;
                 const int tt = (int)(t - f * per_frame_tiles);
                 const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-                uint32_t* Et = edge_bits + t * kTileWords;            // tile-major planes: 64 words per tile
-                const uint32_t* Ct = cand_bits + t * kTileWords;
-                const bool has_left = tx > 0, has_right = tx + 1 < tiles_x;
-                // every load of the tile and of its ring is issued before the first use.  Rows beyond the image
-                // and the second word of a last odd column hold 0 in both planes.
-                const uint2 cw = reinterpret_cast<const uint2*>(Ct)[lane];
-                const uint2 ew = reinterpret_cast<const uint2*>(Et)[lane];
-                const uint32_t c_lo = cw.x, c_hi = cw.y, e_lo = ew.x, e_hi = ew.y;
-                const uint32_t e_l = has_left ? Et[-kTileWords + 2 * lane + 1] : 0u;   // word 1 of the left tile
-                const uint32_t e_r = has_right ? Et[kTileWords + 2 * lane] : 0u;       // word 0 of the right tile
-                // ring rows above / below the tile: lane 0 / lane 31 fetch them (row 31 of the tile above,
-                // row 0 of the tile below)
-                const bool ring_in = (lane == 0 && ty > 0) || (lane == 31 && ty + 1 < tiles_y);
-                uint32_t g_lo = 0, g_hi = 0, g_l = 0, g_r = 0;
-                if (ring_in) {
-                    const uint32_t* pe = (lane == 0) ? Et - (int64_t)tiles_x * kTileWords + 62
-                                                     : Et + (int64_t)tiles_x * kTileWords;
-                    g_lo = pe[0];
-                    g_hi = pe[1];
-                    if (has_left) g_l = pe[-kTileWords + 1];
-                    if (has_right) g_r = pe[kTileWords];
-                }
+                uint32_t* Et = edge_bits + t * kTileWords;
+                const uint32_t c_lo = cur.cw.x, c_hi = cur.cw.y, e_lo = cur.ew.x, e_hi = cur.ew.y;
+                const uint32_t e_l = cur.e_l, e_r = cur.e_r;
+                const uint32_t g_lo = cur.g_lo, g_hi = cur.g_hi, g_l = cur.g_l, g_r = cur.g_r;
                 const unsigned long long c = (unsigned long long)c_lo | ((unsigned long long)c_hi << 32);
                 unsigned long long e = (unsigned long long)e_lo | ((unsigned long long)e_hi << 32);
                 // weak pixels left in this tile?  (warp-uniform exit: nothing can change)
@@ -491,100 +516,75 @@ __global__ void __launch_bounds__(256) psd_edge_dilate_any_bits_kernel(const uin
     dil[f * per_frame + i] = o;
 }
 
-// the usual kernel sizes (k = 2 R + 1 <= 17), dilation AND the SAD in one pass.  A thread owns one word column of
-// a band of kDilBand rows and walks a chunk of kDilChunk consecutive frames; per frame it marches down the band
-// with the last 2 R + 1 horizontally dilated rows in registers (the row loop is fully unrolled, so the ring slots
-// and the 32 words of the previous frame's dilated column are register names), stores the dilated word and
-// counts the bits that differ from the previous frame's word - which it still holds.  The first frame of a chunk
-// gets its predecessor by dilating it once more (1 / kDilChunk extra work) or, for the first frame of the batch,
-// from the carry plane.  Consecutive lanes own consecutive word columns of the same band, so the left / right
-// neighbour words come from the neighbouring LANES (two shuffles) and only the first and last lane of a warp
-// load theirs: one load per output word.  Every lane runs the same steps; rows, frames and lanes outside the
-// work are predicates, not branches.
+// the usual kernel sizes (k = 2 R + 1 <= 17): a thread owns one word column of a band of kDilBand rows and
+// marches down it with the last 2 R + 1 horizontally dilated rows in registers (the row loop is unrolled
+// 2 R + 1 times so the ring slots are register names).  Consecutive lanes own consecutive word columns of the
+// same band, so the left / right neighbour words come from the neighbouring LANES (two shuffles) and only the
+// first and last lane of a warp load theirs: one load per output word (a tile-major load touches 16 sectors
+// per warp, three of them per row cost more than the row-major version of this kernel did).  Every lane runs
+// the same kDilBand + 2 R steps; rows and lanes outside the image are predicates, not branches.
 constexpr int kDilBand = 32;
-constexpr int kDilChunk = 8;
 
 template <int R>
-__global__ void __launch_bounds__(256, PSD_DILATE_CTAS) psd_edge_dilate_sad_kernel(const uint32_t* __restrict__ in,
-                                                                  uint32_t* __restrict__ out,
-                                                                  const uint32_t* __restrict__ carry, int n, int H,
-                                                                  int Wq, int tiles_x, int64_t tile_words_per_frame,
-                                                                  int bands, int64_t n_threads,
-                                                                  uint32_t last_word_mask, int have_prev,
-                                                                  psd_frame_sums* __restrict__ sums) {
+__global__ void __launch_bounds__(256) psd_edge_dilate_bits_kernel(const uint32_t* __restrict__ in,
+                                                                   uint32_t* __restrict__ out, int H, int Wq,
+                                                                   int tiles_x, int64_t tile_words_per_frame,
+                                                                   int bands, int64_t n_threads,
+                                                                   uint32_t last_word_mask) {
     const int64_t gid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = gid0 < n_threads;
-    const int64_t gid = active ? gid0 : n_threads - 1;   // idle lanes shadow the last thread and contribute nothing
+    const int64_t gid = active ? gid0 : n_threads - 1;   // idle lanes shadow the last thread and store nothing
     const int lane = threadIdx.x & 31;
     const int wq = (int)(gid % Wq);
     const int band = (int)((gid / Wq) % bands);
-    const int chunk = (int)(gid / ((int64_t)Wq * bands));
+    const int64_t f = gid / ((int64_t)Wq * bands);
+    const uint32_t* src = in + f * tile_words_per_frame;
+    uint32_t* dst = out + f * (int64_t)H * Wq + wq;
     const uint32_t keep = (wq == Wq - 1) ? last_word_mask : 0xFFFFFFFFu;   // columns >= W stay 0
     const bool has_prv = wq > 0, has_nxt = wq + 1 < Wq;
     const bool load_prv = has_prv && lane == 0, load_nxt = has_nxt && lane == 31;
-    const int y0 = band * kDilBand;
-    const int64_t per_frame = (int64_t)H * Wq;
+    auto hdil = [&](int y) -> uint32_t {
+        const bool row_in = y >= 0 && y < H;
+        const uint32_t cur = row_in ? tiled_word(src, tiles_x, y, wq) : 0u;
+        uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, cur, 1), nxt = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+        if (load_prv) prv = row_in ? tiled_word(src, tiles_x, y, wq - 1) : 0u;
+        if (load_nxt) nxt = row_in ? tiled_word(src, tiles_x, y, wq + 1) : 0u;
+        if (!has_prv) prv = 0u;
+        if (!has_nxt) nxt = 0u;
+        uint32_t o = cur;
+#pragma unroll
+        for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
+        return o & keep;
+    };
     constexpr int K = 2 * R + 1;
-    uint32_t prev[kDilBand];   // the previous frame's dilated words of this column
-    const int f_first = chunk * kDilChunk;
-    // lanes of one warp can sit in two chunks (a warp straddles the end of a frame's thread range)
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, chunk);
-    const bool leader = lane == __ffs(peers) - 1;
-
-    // step -1 rebuilds the predecessor of the chunk's first frame (or takes it from the carry plane)
+    uint32_t ring[K];
+    const int y0 = band * kDilBand;
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
 #pragma unroll 1
-    for (int step = -1; step < kDilChunk; ++step) {
-        const int f = f_first + step;
-        const bool frame_in = f >= 0 && f < n;
-        const bool from_carry = f < 0;                         // only chunk 0, step -1
-        const bool counted = step >= 0 && frame_in && active && (f > 0 || have_prev);
-        const uint32_t* src = in + (int64_t)(frame_in ? f : 0) * tile_words_per_frame;
-        auto hdil = [&](int y) -> uint32_t {
-            const bool row_in = frame_in && y >= 0 && y < H;
-            const uint32_t cur = row_in ? tiled_word(src, tiles_x, y, wq) : 0u;
-            uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, cur, 1), nxt = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
-            if (load_prv) prv = row_in ? tiled_word(src, tiles_x, y, wq - 1) : 0u;
-            if (load_nxt) nxt = row_in ? tiled_word(src, tiles_x, y, wq + 1) : 0u;
-            if (!has_prv) prv = 0u;
-            if (!has_nxt) nxt = 0u;
-            uint32_t o = cur;
+    for (int yo = 0; yo < kDilBand; yo += K) {
 #pragma unroll
-            for (int s = 1; s <= R; ++s) o |= __funnelshift_r(cur, nxt, s) | __funnelshift_l(prv, cur, s);
-            return o & keep;
-        };
-        uint32_t ring[K];
+        for (int j = 0; j < K; ++j) {
+            if (yo + j < kDilBand) {
+                const int y = y0 + yo + j;
+                ring[(K - 1 + j) % K] = hdil(y + R);
+                uint32_t o = 0;
 #pragma unroll
-        for (int i = 0; i < K - 1; ++i) ring[i] = hdil(y0 - R + i);
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int j = 0; j < kDilBand; ++j) {
-            const int y = y0 + j;
-            ring[(K - 1 + j) % K] = hdil(y + R);
-            uint32_t o = 0;
-#pragma unroll
-            for (int i = 0; i < K; ++i) o |= ring[i];
-            if (from_carry) o = (have_prev && y < H) ? carry[(int64_t)y * Wq + wq] : 0u;
-            if (counted && y < H) cnt += __popc(o ^ prev[j]);
-            prev[j] = o;
-            if (step >= 0 && frame_in && active && y < H) out[f * per_frame + (int64_t)y * Wq + wq] = o;
+                for (int i = 0; i < K; ++i) o |= ring[i];
+                if (active && y < H) dst[(int64_t)y * Wq] = o;
+            }
         }
-        cnt = __reduce_add_sync(peers, cnt);
-        if (leader && cnt && step >= 0 && frame_in)
-            atomicAdd(reinterpret_cast<unsigned long long*>(&sums[f].sad_edges), 255ull * cnt);
     }
 }
 
 template <int R>
-static void launch_dilate_sad(const EdgeBuffers& b, int n, int H, int Wq, uint32_t mask, bool have_prev,
-                              psd_frame_sums* sums, cudaStream_t stream) {
+static void launch_dilate(const uint32_t* in, uint32_t* out, int n, int H, int Wq, uint32_t mask, cudaStream_t stream) {
     const int bands = (H + kDilBand - 1) / kDilBand;
-    const int chunks = (n + kDilChunk - 1) / kDilChunk;
     const int tiles_x = (Wq + 1) / 2;
     const int64_t tile_words = (int64_t)tiles_x * ((H + kHystTileH - 1) / kHystTileH) * kTileWords;
-    const int64_t n_threads = (int64_t)Wq * bands * chunks;
-    psd_edge_dilate_sad_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(
-        b.bits_in, b.bits_dil, b.carry_bits, n, H, Wq, tiles_x, tile_words, bands, n_threads, mask, have_prev ? 1 : 0,
-        sums);
+    const int64_t n_threads = (int64_t)Wq * bands * n;
+    psd_edge_dilate_bits_kernel<R><<<(unsigned)((n_threads + 255) / 256), 256, 0, stream>>>(
+        in, out, H, Wq, tiles_x, tile_words, bands, n_threads, mask);
 }
 
 __global__ void __launch_bounds__(256) psd_edge_sad_bits_kernel(const uint32_t* __restrict__ dil,
@@ -687,26 +687,25 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     const int r = ksize / 2;
     const uint32_t last_mask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu;
     switch (r) {
-        case 1: launch_dilate_sad<1>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 2: launch_dilate_sad<2>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 3: launch_dilate_sad<3>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 4: launch_dilate_sad<4>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 5: launch_dilate_sad<5>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 6: launch_dilate_sad<6>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 7: launch_dilate_sad<7>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        case 8: launch_dilate_sad<8>(b, n, H, Wq, last_mask, have_prev, sums, stream); break;
-        default: {   // any other kernel size: one thread per output word, then the SAD
+        case 1: launch_dilate<1>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 2: launch_dilate<2>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 3: launch_dilate<3>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 4: launch_dilate<4>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 5: launch_dilate<5>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 6: launch_dilate<6>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 7: launch_dilate<7>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        case 8: launch_dilate<8>(b.bits_in, b.bits_dil, n, H, Wq, last_mask, stream); break;
+        default: {   // any other kernel size
             dim3 cgd((unsigned)((per_frame + 255) / 256), (unsigned)n);
             psd_edge_dilate_any_bits_kernel<<<cgd, 256, 0, stream>>>(b.bits_in, b.bits_dil, H, Wq, (Wq + 1) / 2,
                                                                      edge_tile_words(W, H), r, last_mask);
-            PSD_CHECK_LAUNCH();
-            dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
-            psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
-            count_launch(1);
         }
     }
     PSD_CHECK_LAUNCH();
-    count_launch(1);
+    dim3 sg((unsigned)min((int64_t)64, (per_frame + 255) / 256), (unsigned)n);
+    psd_edge_sad_bits_kernel<<<sg, 256, 0, stream>>>(b.bits_dil, b.carry_bits, per_frame, have_prev ? 1 : 0, sums);
+    PSD_CHECK_LAUNCH();
+    count_launch(2);
     PSD_CUDA(cudaMemcpyAsync(b.carry_bits, b.bits_dil + (int64_t)(n - 1) * per_frame,
                              (size_t)per_frame * 4, cudaMemcpyDeviceToDevice, stream));
     return PSD_OK;

@@ -21,6 +21,14 @@ namespace psd {
 __device__ __forceinline__ uint32_t gray_bgr(uint32_t b, uint32_t g, uint32_t r) {
     return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
 }
+// the same from a register holding (B, G, R, x) bytes: two IDP4A on the weights' high and low bytes
+// (3735 = 14 * 256 + 151, 19235 = 75 * 256 + 35, 9798 = 38 * 256 + 70; 64 * 256 = the rounding constant)
+__device__ __forceinline__ uint32_t gray_word(uint32_t px) {
+    const uint32_t hi = __dp4a(px, 0x00264B0Eu, 64u);
+    return (__dp4a(px, 0x00462397u, hi << 8)) >> 15;
+}
+// byte -> float32 without the conversion unit: 0x4B000000 | g is 2^23 + g
+__device__ __forceinline__ float byte_to_float(uint32_t g) { return __fadd_rn(__uint_as_float(0x4B000000u | g), -8388608.0f); }
 
 // The horizontal pass.  A CTA takes a block of consecutive source rows of one frame (256 / n of them):
 //   1. all threads pull the block - it is contiguous in memory - 16 pixels (three 16-byte loads) at a time,
@@ -36,6 +44,7 @@ __global__ void __launch_bounds__(256) psd_hash_rows_kernel(const uint8_t* __res
                                                             const int32_t* __restrict__ xstart,
                                                             const int32_t* __restrict__ xsi,
                                                             const float* __restrict__ xalpha,
+                                                            const int32_t* __restrict__ xmid,
                                                             float* __restrict__ rowbuf) {
     extern __shared__ __align__(16) uint8_t sgray[];   // [rows_per_cta][pitch]
     const int tid = threadIdx.x;
@@ -55,10 +64,10 @@ __global__ void __launch_bounds__(256) psd_hash_rows_kernel(const uint8_t* __res
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {   // 4 pixels = 12 bytes = words 3 g4 .. 3 g4 + 2
                 const uint32_t w0 = w[3 * g4], w1 = w[3 * g4 + 1], w2 = w[3 * g4 + 2];
-                const uint32_t g0 = gray_bgr(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
-                const uint32_t g1 = gray_bgr(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
-                const uint32_t g2 = gray_bgr((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
-                const uint32_t g3 = gray_bgr((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+                const uint32_t g0 = gray_word(w0);                              // bytes 0 1 2 (3 ignored: weight 0)
+                const uint32_t g1 = gray_word(__byte_perm(w0, w1, 0x0543));     // bytes 3 4 5
+                const uint32_t g2 = gray_word(__byte_perm(w1, w2, 0x0432));     // bytes 6 7 8
+                const uint32_t g3 = gray_word(w2 >> 8);                         // bytes 9 10 11
                 dst[g4] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
             }
         }
@@ -81,11 +90,18 @@ __global__ void __launch_bounds__(256) psd_hash_rows_kernel(const uint8_t* __res
         for (int x = dx * sxw; x < (dx + 1) * sxw; ++x) s += srow[x];
         *out = __uint_as_float(s);
     } else {
+        // first (partial) tap, the run of whole pixels, last (partial) tap - in source order
         float buf = 0.0f;
-        const int k1 = xstart[dx + 1];
-#pragma unroll 4
-        for (int k = xstart[dx]; k < k1; ++k)
-            buf = __fadd_rn(buf, __fmul_rn((float)srow[xsi[k]], xalpha[k]));
+        const int k0 = xstart[dx], k1 = xstart[dx + 1];
+        const int km = xmid[2 * dx], nm = xmid[2 * dx + 1];
+        for (int k = k0; k < km; ++k) buf = __fadd_rn(buf, __fmul_rn(byte_to_float(srow[xsi[k]]), xalpha[k]));
+        if (nm > 0) {
+            const uint8_t* sp = srow + xsi[km];
+            const float am = xalpha[km];
+#pragma unroll 8
+            for (int i = 0; i < nm; ++i) buf = __fadd_rn(buf, __fmul_rn(byte_to_float(sp[i]), am));
+        }
+        for (int k = km + nm; k < k1; ++k) buf = __fadd_rn(buf, __fmul_rn(byte_to_float(srow[xsi[k]]), xalpha[k]));
         *out = buf;
     }
 }
@@ -280,6 +296,19 @@ int hash_plan_create(HashPlan* p, int W, int H, int size, int lowpass, int max_b
     int rc = upload(st, &p->xstart); if (rc) return rc;
     rc = upload(si, &p->xsi); if (rc) return rc;
     rc = upload(al, &p->xalpha); if (rc) return rc;
+    {   // the whole-pixel taps of a column are consecutive source pixels with one common weight
+        std::vector<int32_t> mid((size_t)2 * n);
+        const double scale = (double)W / n;
+        for (int dx = 0; dx < n; ++dx) {
+            const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+            int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+            sx2 = std::min(sx2, W - 1);
+            sx1 = std::min(sx1, sx2);
+            mid[2 * dx] = st[dx] + ((sx1 - fsx1 > 1e-3) ? 1 : 0);
+            mid[2 * dx + 1] = std::max(0, sx2 - sx1);
+        }
+        rc = upload(mid, &p->xmid); if (rc) return rc;
+    }
     area_tab(H, n, st, si, al);
     rc = upload(st, &p->ystart); if (rc) return rc;
     rc = upload(si, &p->ysi); if (rc) return rc;
@@ -302,7 +331,7 @@ int hash_plan_create(HashPlan* p, int W, int H, int size, int lowpass, int max_b
 }
 
 void hash_plan_destroy(HashPlan* p) {
-    cudaFree(p->xstart); cudaFree(p->xsi); cudaFree(p->xalpha); cudaFree(p->ystart); cudaFree(p->ysi);
+    cudaFree(p->xstart); cudaFree(p->xsi); cudaFree(p->xmid); cudaFree(p->xalpha); cudaFree(p->ystart); cudaFree(p->ysi);
     cudaFree(p->ybeta); cudaFree(p->cosn); cudaFree(p->rowbuf);
     *p = HashPlan{};
 }
@@ -317,7 +346,7 @@ int launch_hash(const HashPlan& p, const uint8_t* frames, int64_t frame_stride, 
     PSD_CUDA(cudaFuncSetAttribute(psd_hash_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     dim3 rgrid((unsigned)((H + rows_per_cta - 1) / rows_per_cta), (unsigned)n_frames);
     psd_hash_rows_kernel<<<rgrid, 256, smem_rows, stream>>>(frames, frame_stride, W, H, p.n, rows_per_cta, pitch, p.fast,
-                                                            p.xstart, p.xsi, p.xalpha, p.rowbuf);
+                                                            p.xstart, p.xsi, p.xalpha, p.xmid, p.rowbuf);
     PSD_CHECK_LAUNCH();
     FoldPlan fp{};
     fp.levels = p.levels;

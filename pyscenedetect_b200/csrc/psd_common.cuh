@@ -104,6 +104,7 @@ struct HashPlan {        // per-engine tables for one (frame size, hash size, lo
     int fast = 0;        // both area scale factors are integers
     int area_w = 0, area_h = 0;
     int32_t *xstart = nullptr, *xsi = nullptr, *ystart = nullptr, *ysi = nullptr;
+    int32_t *xmid = nullptr;  // [n][2]: table index of the first whole-pixel tap of a destination column, their count
     float *xalpha = nullptr, *ybeta = nullptr;
     double* cosn = nullptr;   // [4n] cos(pi k / 2n)
     int levels = 1, len[8] = {0}, off[8] = {0};  // folded levels of a length-n vector (hash_kernels.cu:FoldPlan)
