@@ -31,7 +31,7 @@ namespace cg = cooperative_groups;
 #define PSD_CLASSIFY_CTAS 3
 #endif
 #ifndef PSD_HYST_CTAS
-#define PSD_HYST_CTAS 3   // 85 registers: room for the next tile's loads
+#define PSD_HYST_CTAS 4   // (3 CTAs x 85 registers measured slower than 4 x 64 even with the next tile's loads in flight)
 #endif
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
@@ -323,7 +323,7 @@ __device__ __forceinline__ TileLoad load_tile(const uint32_t* __restrict__ edge_
 }
 
 #if PSD_HYST_STATS   // alt build for tools/gpu_*.sh: per-round tile counts and times of the first launches
-__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512];
+__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512], g_hs_timeA[512], g_hs_t0;
 __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { if (lane == 0 && (round) < 512) atomicAdd(&arr[round], 1ull); } while (0)
 #else
@@ -346,6 +346,9 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
     const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
     const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles);
 
+#if PSD_HYST_STATS
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_hs_t0));
+#endif
     for (int round = 0; round < 100000; ++round) {
         // ---- A: compact the dirty tiles into the work list (dirty tiles cluster - whole frames, image regions -
         //         so visiting them straight from the owner's run leaves most warps idle: round times followed
@@ -384,6 +387,13 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
         if (blockIdx.x == 0 && threadIdx.x == 0) counts[(round + 1) % 3] = 0;
         __threadfence();
         grid.sync();
+#if PSD_HYST_STATS
+        if (blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            g_hs_timeA[round] = now;
+        }
+#endif
         const int64_t n_work = *(volatile int32_t*)count;
         if (n_work == 0) {
 #if PSD_HYST_STATS
@@ -392,9 +402,9 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
                 if (l == 4 || l == 9) {   // a warm launch
                     printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round, (long long)n_tiles, (int)gridDim.x);
                     for (int r = 0; r < round && r < 512; ++r)
-                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  +%llu ns\n", r,
+                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  A %llu ns  B %llu ns\n", r,
                                g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
-                               r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
+                               g_hs_timeA[r] - (r ? g_hs_time[r - 1] : g_hs_t0), g_hs_time[r] - g_hs_timeA[r]);
                 }
                 for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
             }
