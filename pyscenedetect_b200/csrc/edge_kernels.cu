@@ -31,7 +31,10 @@ namespace cg = cooperative_groups;
 #define PSD_CLASSIFY_CTAS 3
 #endif
 #ifndef PSD_HYST_CTAS
-#define PSD_HYST_CTAS 4   // (3 CTAs x 85 registers measured slower than 4 x 64 even with the next tile's loads in flight)
+#define PSD_HYST_CTAS 5
+#endif
+#ifndef PSD_HYST_CHUNKS
+#define PSD_HYST_CHUNKS 1   // 1: runs of 32 tiles dealt round-robin to the warps; 0: one contiguous run per warp
 #endif
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
@@ -286,44 +289,8 @@ __device__ __forceinline__ unsigned long long run_fill(unsigned long long t, uns
     return up | dn;
 }
 
-// what a warp pulls for one tile: lane r holds row r of C and E, the E words left and right of the row, and
-// (lanes 0 and 31) the ring row above / below with its two corner words.  Tile-major planes: the tile is 64
-// consecutive words, one 256-byte request per plane; rows beyond the image and the second word of a last odd
-// column hold 0 in both planes.
-struct TileLoad {
-    int64_t t;
-    uint2 cw, ew;
-    uint32_t e_l, e_r, g_lo, g_hi, g_l, g_r;
-};
-
-__device__ __forceinline__ TileLoad load_tile(const uint32_t* __restrict__ edge_bits, const uint32_t* __restrict__ cand_bits,
-                                              int64_t t, int64_t per_frame_tiles, int tiles_x, int tiles_y, int lane) {
-    TileLoad d;
-    d.t = t;
-    const int tt = (int)(t % per_frame_tiles);
-    const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-    const uint32_t* Et = edge_bits + t * kTileWords;
-    const uint32_t* Ct = cand_bits + t * kTileWords;
-    const bool has_left = tx > 0, has_right = tx + 1 < tiles_x;
-    d.cw = reinterpret_cast<const uint2*>(Ct)[lane];
-    d.ew = reinterpret_cast<const uint2*>(Et)[lane];
-    d.e_l = has_left ? Et[-kTileWords + 2 * lane + 1] : 0u;   // word 1 of the left tile
-    d.e_r = has_right ? Et[kTileWords + 2 * lane] : 0u;       // word 0 of the right tile
-    // ring rows: lane 0 fetches row 31 of the tile above, lane 31 row 0 of the tile below
-    const bool ring_in = (lane == 0 && ty > 0) || (lane == 31 && ty + 1 < tiles_y);
-    d.g_lo = d.g_hi = d.g_l = d.g_r = 0u;
-    if (ring_in) {
-        const uint32_t* pe = (lane == 0) ? Et - (int64_t)tiles_x * kTileWords + 62 : Et + (int64_t)tiles_x * kTileWords;
-        d.g_lo = pe[0];
-        d.g_hi = pe[1];
-        if (has_left) d.g_l = pe[-kTileWords + 1];
-        if (has_right) d.g_r = pe[kTileWords];
-    }
-    return d;
-}
-
 #if PSD_HYST_STATS   // alt build for tools/gpu_*.sh: per-round tile counts and times of the first launches
-__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512], g_hs_timeA[512], g_hs_t0;
+__device__ unsigned long long g_hs_visit[512], g_hs_work[512], g_hs_change[512], g_hs_time[512], g_hs_iter[512];
 __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { if (lane == 0 && (round) < 512) atomicAdd(&arr[round], 1ull); } while (0)
 #else
@@ -332,104 +299,71 @@ __device__ int g_hs_launch;
 
 __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
-                                                            uint8_t* __restrict__ dirty /* [n_tiles] */,
-                                                            int32_t* __restrict__ worklist /* [n_tiles] */,
-                                                            int32_t* __restrict__ counts /* [3] */,
-                                                            int tiles_x, int tiles_y, int64_t n_tiles) {
+                                                            uint8_t* __restrict__ dirty /* [2][n_tiles] */,
+                                                            int32_t* __restrict__ flags /* [3] */, int W, int H,
+                                                            int Wq, int tiles_x, int tiles_y, int64_t n_tiles) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ int s_cnt[9];   // phase A: dirty tiles per warp -> exclusive prefix; [8] = the CTA's base in the list
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t per_frame_tiles = (int64_t)tiles_x * tiles_y;
-    // phase A of a round: a warp scans the dirty bytes of a contiguous run of tiles, 32 at a time, one per lane
+    // Tiles are dealt to the warps in runs of 32 (their dirty bytes are read 32 at a time, one per lane, and a
+    // warp visits the dirty ones of a run one after the other, so a change walks along the run within the round).
+    // Round-robin over the runs: the heavy frames of a batch are spread over all warps.  (A compacted work list
+    // per round - perfectly even counts, but neighbouring tiles visited by different warps at the same time -
+    // took twice as long: profiles/r02i_edge_ab_summary.txt.)
+#if PSD_HYST_CHUNKS
+    const int64_t t_begin = warp0 * 32, t_end = n_tiles, t_step = n_warps * 32;
+#else
     const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
-    const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles);
+    const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles), t_step = 32;
+#endif
 
-#if PSD_HYST_STATS
-    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_hs_t0));
-#endif
     for (int round = 0; round < 100000; ++round) {
-        // ---- A: compact the dirty tiles into the work list (dirty tiles cluster - whole frames, image regions -
-        //         so visiting them straight from the owner's run leaves most warps idle: round times followed
-        //         the busiest warp, profiles/r02i_edge_ab_summary.txt) ----
-        int32_t* count = counts + round % 3;
-        // one atomic per CTA and round on the list length (one per 32 tiles serialised ~16 k same-address
-        // atomics per round at L2 and doubled the kernel's time): count, reserve, then write
-        int n_mine = 0;
-        for (int64_t base = t_begin; base < t_end; base += 32) {
-            const int64_t mine = base + lane;
-            const bool need = mine < t_end && dirty[mine] != 0;
-            n_mine += __popc(__ballot_sync(0xFFFFFFFFu, need));
-        }
-        if (lane == 0) s_cnt[threadIdx.x >> 5] = n_mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-            s_cnt[8] = tot ? atomicAdd(count, tot) : 0;
-        }
-        __syncthreads();
-        int off = s_cnt[8] + s_cnt[threadIdx.x >> 5];
-        __syncthreads();   // s_cnt is rewritten next round
-        for (int64_t base = t_begin; base < t_end && n_mine; base += 32) {
-            const int64_t mine = base + lane;
-            bool need = mine < t_end;
-            if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
-                need = dirty[mine] != 0;
-                if (need) dirty[mine] = 0;
-            }
-            const uint32_t todo = __ballot_sync(0xFFFFFFFFu, need);
-            if (need) worklist[off + __popc(todo & ((1u << lane) - 1u))] = (int32_t)mine;
-            off += __popc(todo);
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) counts[(round + 1) % 3] = 0;
-        __threadfence();
-        grid.sync();
-#if PSD_HYST_STATS
-        if (blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-            g_hs_timeA[round] = now;
-        }
-#endif
-        const int64_t n_work = *(volatile int32_t*)count;
-        if (n_work == 0) {
-#if PSD_HYST_STATS
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                const int l = atomicAdd(&g_hs_launch, 1);
-                if (l == 4 || l == 9) {   // a warm launch
-                    printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round, (long long)n_tiles, (int)gridDim.x);
-                    for (int r = 0; r < round && r < 512; ++r)
-                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  A %llu ns  B %llu ns\n", r,
-                               g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
-                               g_hs_timeA[r] - (r ? g_hs_time[r - 1] : g_hs_t0), g_hs_time[r] - g_hs_timeA[r]);
+        uint8_t* dcur = dirty + (int64_t)(round & 1) * n_tiles;
+        uint8_t* dnext = dirty + (int64_t)((round + 1) & 1) * n_tiles;
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[(round + 1) % 3] = 0;
+        bool warp_changed = false;
+        for (int64_t base = t_begin; base < t_end; base += t_step) {
+            uint32_t todo;  // bit l: tile base + l needs a visit this round
+            {
+                const int64_t mine = base + lane;
+                bool need = mine < t_end;
+                if (need) {  // round 0: the classify kernel flagged the tiles that hold weak candidates
+                    need = dcur[mine] != 0;
+                    if (need) dcur[mine] = 0;
                 }
-                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
+                todo = __ballot_sync(0xFFFFFFFFu, need);
             }
-#endif
-            break;
-        }
-        // ---- B: every warp takes every n_warps-th entry of the list.  A warp works through its tiles one after
-        //         the other and a tile starts with two dependent trips to L2 (list entry, then the tile and its
-        //         ring): the loads of the NEXT tile are issued before the fill loop of the current one. ----
-        {
-            TileLoad cur, nxt;
-            int64_t wi = warp0;
-            if (wi < n_work) cur = load_tile(edge_bits, cand_bits, worklist[wi], per_frame_tiles, tiles_x, tiles_y, lane);
-            for (; wi < n_work; wi += n_warps, cur = nxt) {
-                if (wi + n_warps < n_work)
-                    nxt = load_tile(edge_bits, cand_bits, worklist[wi + n_warps], per_frame_tiles, tiles_x, tiles_y, lane);
-                const int64_t t = cur.t;
+            while (todo) {
+                const int64_t t = base + __ffs(todo) - 1;
+                todo &= todo - 1;
                 HS_COUNT(g_hs_visit, round);
                 const int64_t f = t / per_frame_tiles;
                 const int tt = (int)(t - f * per_frame_tiles);
                 const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-                uint32_t* Et = edge_bits + t * kTileWords;
-                const uint32_t c_lo = cur.cw.x, c_hi = cur.cw.y, e_lo = cur.ew.x, e_hi = cur.ew.y;
-                const uint32_t e_l = cur.e_l, e_r = cur.e_r;
-                const uint32_t g_lo = cur.g_lo, g_hi = cur.g_hi, g_l = cur.g_l, g_r = cur.g_r;
+                uint32_t* Et = edge_bits + t * kTileWords;            // tile-major planes: 64 words per tile
+                const uint32_t* Ct = cand_bits + t * kTileWords;
+                const bool has_left = tx > 0, has_right = tx + 1 < tiles_x;
+                // every load of the tile and of its ring is issued before the first use.  Rows beyond the image
+                // and the second word of a last odd column hold 0 in both planes.
+                const uint2 cw = reinterpret_cast<const uint2*>(Ct)[lane];
+                const uint2 ew = reinterpret_cast<const uint2*>(Et)[lane];
+                const uint32_t c_lo = cw.x, c_hi = cw.y, e_lo = ew.x, e_hi = ew.y;
+                const uint32_t e_l = has_left ? Et[-kTileWords + 2 * lane + 1] : 0u;   // word 1 of the left tile
+                const uint32_t e_r = has_right ? Et[kTileWords + 2 * lane] : 0u;       // word 0 of the right tile
+                // ring rows above / below the tile: lane 0 / lane 31 fetch them (row 31 of the tile above,
+                // row 0 of the tile below)
+                const bool ring_in = (lane == 0 && ty > 0) || (lane == 31 && ty + 1 < tiles_y);
+                uint32_t g_lo = 0, g_hi = 0, g_l = 0, g_r = 0;
+                if (ring_in) {
+                    const uint32_t* pe = (lane == 0) ? Et - (int64_t)tiles_x * kTileWords + 62
+                                                     : Et + (int64_t)tiles_x * kTileWords;
+                    g_lo = pe[0];
+                    g_hi = pe[1];
+                    if (has_left) g_l = pe[-kTileWords + 1];
+                    if (has_right) g_r = pe[kTileWords];
+                }
                 const unsigned long long c = (unsigned long long)c_lo | ((unsigned long long)c_hi << 32);
                 unsigned long long e = (unsigned long long)e_lo | ((unsigned long long)e_hi << 32);
                 // weak pixels left in this tile?  (warp-uniform exit: nothing can change)
@@ -462,16 +396,18 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
                 const bool changed = e != e_in;
                 if (changed) reinterpret_cast<uint2*>(Et)[lane] = make_uint2((uint32_t)e, (uint32_t)(e >> 32));
                 if (__ballot_sync(0xFFFFFFFFu, changed) != 0u) {
+                    warp_changed = true;
                     HS_COUNT(g_hs_change, round);
                     // the ring of the 8 neighbours may have changed: they look again next round
                     if (lane < 9 && lane != 4) {
                         const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
                         if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x)
-                            dirty[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
+                            dnext[f * per_frame_tiles + (int64_t)ny * tiles_x + nx] = 1;
                     }
                 }
             }
         }
+        if (warp_changed && lane == 0) atomicOr(&flags[round % 3], 1);
         __threadfence();
         grid.sync();
 #if PSD_HYST_STATS
@@ -481,6 +417,22 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
             g_hs_time[round] = now;
         }
 #endif
+        if (*(volatile int32_t*)&flags[round % 3] == 0) {
+#if PSD_HYST_STATS
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const int l = atomicAdd(&g_hs_launch, 1);
+                if (l == 4 || l == 9) {   // a warm launch
+                    printf("hyst launch %d: %d rounds, %lld tiles, grid %d\n", l, round + 1, (long long)n_tiles, (int)gridDim.x);
+                    for (int r = 0; r <= round && r < 512; ++r)
+                        printf("  round %d: visited %llu worked %llu changed %llu iterations %llu  +%llu ns\n", r,
+                               g_hs_visit[r], g_hs_work[r], g_hs_change[r], g_hs_iter[r],
+                               r ? g_hs_time[r] - g_hs_time[r - 1] : 0ull);
+                }
+                for (int r = 0; r < 512; ++r) g_hs_visit[r] = g_hs_work[r] = g_hs_change[r] = g_hs_iter[r] = 0ull;
+            }
+#endif
+            break;
+        }
     }
 }
 
@@ -660,7 +612,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         // (bytes of the planes that no strip writes - beyond the last strip, below the last row - were zeroed
         // when the planes were allocated and nothing ever sets them)
         const int64_t n_tiles0 = (int64_t)((Wq + 1) / 2) * bands * n;  // bands == hysteresis tile rows
-        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)n_tiles0, stream));
+        PSD_CUDA(cudaMemsetAsync(b.dirty, 0, (size_t)2 * n_tiles0, stream));
         if ((W & 7) == 0)
             psd_canny_classify_pairs_kernel<true><<<blocks, cblock, 0, stream>>>(b.vplane, b.thresholds, b.bits_in, b.cand,
                                                                               b.dirty, W, H, Wq, strips, bands, n_threads);
@@ -688,9 +640,9 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
         uint32_t* e_ptr = b.bits_in;
         const uint32_t* c_ptr = b.cand;
         uint8_t* d_ptr = b.dirty;
-        int32_t* l_ptr = b.worklist;
         int32_t* f_ptr = b.hyst_flags;
-        void* args[] = {&e_ptr, &c_ptr, &d_ptr, &l_ptr, &f_ptr, &tiles_x, &tiles_y, &n_tiles};
+        int w_ = W, h_ = H, wq_ = Wq;
+        void* args[] = {&e_ptr, &c_ptr, &d_ptr, &f_ptr, &w_, &h_, &wq_, &tiles_x, &tiles_y, &n_tiles};
         PSD_CUDA(cudaLaunchCooperativeKernel((const void*)psd_hyst_bits_kernel, dim3(grid), dim3(256), args, 0, stream));
     }
     count_launch(3);

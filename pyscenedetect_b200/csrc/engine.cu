@@ -278,7 +278,7 @@ void psd_engine_destroy(psd_engine* e) {
     hash_plan_destroy(&e->hash);
     cudaFree(e->eb.vplane); cudaFree(e->eb.vhist); cudaFree(e->eb.thresholds); cudaFree(e->eb.cand);
     cudaFree(e->eb.tmp); cudaFree(e->eb.bits_in); cudaFree(e->eb.bits_dil);
-    cudaFree(e->eb.carry_bits); cudaFree(e->eb.dirty); cudaFree(e->eb.worklist); cudaFree(e->eb.hyst_flags);
+    cudaFree(e->eb.carry_bits); cudaFree(e->eb.dirty); cudaFree(e->eb.hyst_flags);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
@@ -383,8 +383,7 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
         ENG_CUDA(cudaMalloc(&e->eb.thresholds, (size_t)e->max_batch * 2 * 4));
         ENG_CUDA(cudaMalloc(&e->eb.hyst_flags, 64));
         const size_t n_tiles = (size_t)e->max_batch * ((e->W + 63) / 64) * ((e->H + 31) / 32);
-        ENG_CUDA(cudaMalloc(&e->eb.dirty, n_tiles));
-        ENG_CUDA(cudaMalloc(&e->eb.worklist, n_tiles * sizeof(int32_t)));
+        ENG_CUDA(cudaMalloc(&e->eb.dirty, 2 * n_tiles));
     }
     {
         int rc = ensure_capacity(e, 4096);

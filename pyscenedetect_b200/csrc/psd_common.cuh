@@ -89,9 +89,8 @@ struct EdgeBuffers {
     uint32_t* bits_dil; // [n][H][Wq] dilated edges, row-major
     uint32_t* carry_bits; // [H][Wq] dilated edges of the predecessor frame
     uint8_t* tmp;       // [P] scratch for debug taps
-    uint8_t* dirty;     // [n][tiles] hysteresis: tiles to (re)visit
-    int32_t* worklist;  // [n][tiles] hysteresis: the dirty tiles of the current round, compacted
-    int32_t* hyst_flags;// [3] hysteresis: length of the work list per round (rotating)
+    uint8_t* dirty;     // [2][n][tiles] hysteresis: tiles to revisit (double-buffered by round parity)
+    int32_t* hyst_flags;// [3] hysteresis: "some tile changed" per round (rotating)
 };
 int launch_edges(const EdgeBuffers& b, int n, int width, int height, int ksize, bool have_prev,
                  psd_frame_sums* sums, cudaStream_t stream);

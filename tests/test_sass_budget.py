@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP) or not os.path.exi
 
 WS_HSV_V7 = "_ZN3psd19psd_score_ws_kernelILj1EEEvNS_9ScoreArgsE"
 CLASSIFY = "_ZN3psd31psd_canny_classify_pairs_kernelILb1EEEvPKhPKiPjS5_Phiiiiil"
-HYST = "_ZN3psd20psd_hyst_bits_kernelEPjPKjPhPiS4_iil"
+HYST = "_ZN3psd20psd_hyst_bits_kernelEPjPKjPhPiiiiiil"
 LINE = re.compile(r"^\s+/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Za-z0-9_.]+)")
 
 
