@@ -23,19 +23,9 @@
 
 namespace cg = cooperative_groups;
 
-#ifndef PSD_CLASSIFY_SWP
-#define PSD_CLASSIFY_SWP 1   // load the row window one row ahead into registers
-#endif
-#ifndef PSD_CLASSIFY_BLOCK
-#define PSD_CLASSIFY_BLOCK 128   // 128 x 3: 163 registers, no spills (256 x 2 caps at 128 and spills ~50 words)
-#define PSD_CLASSIFY_CTAS 3
-#endif
-#ifndef PSD_HYST_CTAS
-#define PSD_HYST_CTAS 5
-#endif
-#ifndef PSD_HYST_CHUNKS
-#define PSD_HYST_CHUNKS 1   // 1: runs of 32 tiles dealt round-robin to the warps; 0: one contiguous run per warp
-#endif
+// classify launch shape: 128 threads x 3 CTAs per SM = 163 registers, no spills (256 x 2 caps at 128 registers
+// and spills ~50 words; measured 3-4 % slower)
+constexpr int kClassifyBlock = 128;
 #ifndef PSD_HYST_STATS
 #define PSD_HYST_STATS 0
 #endif
@@ -103,7 +93,7 @@ constexpr int kBandRows = 32;   // == kHystTileH: a band of the classify kernel 
 constexpr int kTileWords = 64;  // 32 rows x 2 words
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(PSD_CLASSIFY_BLOCK, PSD_CLASSIFY_CTAS) psd_canny_classify_pairs_kernel(
+__global__ void __launch_bounds__(kClassifyBlock, 3) psd_canny_classify_pairs_kernel(
     const uint8_t* __restrict__ vplane, const int32_t* __restrict__ thr, uint32_t* __restrict__ edge_bits,
     uint32_t* __restrict__ cand_bits, uint8_t* __restrict__ tile_dirty, int W, int H, int Wq, int strips,
     int bands, int64_t n_threads) {
@@ -153,18 +143,12 @@ __global__ void __launch_bounds__(PSD_CLASSIFY_BLOCK, PSD_CLASSIFY_CTAS) psd_can
     };
     // Row yy+1 arrives: magnitudes (and, if asked, sectors) of row yy from the sums of rows yy-1 (`so`,
     // replaced by row yy+1 on the way out), yy (`sm`) and yy+1.
-#if PSD_CLASSIFY_SWP
     uint32_t wn[4];   // the window of the next row to arrive, loaded one row early
-#endif
     auto advance = [&](int yy, cp::Sums& so, const cp::Sums& sm, cp::Mags& r, bool want_sectors) {
         uint32_t w[4];
-#if PSD_CLASSIFY_SWP
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = wn[i];
         load_window(yy + 2, wn);
-#else
-        load_window(yy + 1, w);
-#endif
         // the first touch of a row goes to L2 / HBM and four warps per scheduler cannot hide that: pull the line
         // of the row two further down into L1 now (no register, no dependency; +4 % on the edge path)
         if (yy + 3 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (int64_t)(yy + 3) * W + x0));
@@ -239,9 +223,7 @@ __global__ void __launch_bounds__(PSD_CLASSIFY_BLOCK, PSD_CLASSIFY_CTAS) psd_can
         cp::row_sums(w, sa);
         load_window(yb - 1, w);
         cp::row_sums(w, sb);
-#if PSD_CLASSIFY_SWP
         load_window(yb, wn);
-#endif
         advance(yb - 1, sa, sb, r0, false);   // sa: yb-2 -> yb
         advance(yb, sb, sa, r1, true);        // sb: yb-1 -> yb+1
     }
@@ -297,7 +279,7 @@ __device__ int g_hs_launch;
 #define HS_COUNT(arr, round) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
+__global__ void __launch_bounds__(256, 5) psd_hyst_bits_kernel(uint32_t* __restrict__ edge_bits,
                                                             const uint32_t* __restrict__ cand_bits,
                                                             uint8_t* __restrict__ dirty /* [2][n_tiles] */,
                                                             int32_t* __restrict__ flags /* [3] */, int W, int H,
@@ -312,12 +294,8 @@ __global__ void __launch_bounds__(256, PSD_HYST_CTAS) psd_hyst_bits_kernel(uint3
     // Round-robin over the runs: the heavy frames of a batch are spread over all warps.  (A compacted work list
     // per round - perfectly even counts, but neighbouring tiles visited by different warps at the same time -
     // took twice as long: profiles/r02i_edge_ab_summary.txt.)
-#if PSD_HYST_CHUNKS
+    // (one contiguous run per warp: 141.7 k against 148.9 k frames/s)
     const int64_t t_begin = warp0 * 32, t_end = n_tiles, t_step = n_warps * 32;
-#else
-    const int64_t per_warp = (n_tiles + n_warps - 1) / n_warps;
-    const int64_t t_begin = warp0 * per_warp, t_end = min(t_begin + per_warp, n_tiles), t_step = 32;
-#endif
 
     for (int round = 0; round < 100000; ++round) {
         uint8_t* dcur = dirty + (int64_t)(round & 1) * n_tiles;
@@ -607,7 +585,7 @@ int launch_edges(const EdgeBuffers& b, int n, int W, int H, int ksize, bool have
     {
         const int strips = (W + 7) / 8, bands = (H + kBandRows - 1) / kBandRows;
         const int64_t n_threads = (int64_t)strips * bands * n;
-        const unsigned cblock = PSD_CLASSIFY_BLOCK;
+        const unsigned cblock = kClassifyBlock;
         const unsigned blocks = (unsigned)((n_threads + cblock - 1) / cblock);
         // (bytes of the planes that no strip writes - beyond the last strip, below the last row - were zeroed
         // when the planes were allocated and nothing ever sets them)

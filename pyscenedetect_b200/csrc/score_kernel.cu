@@ -347,9 +347,6 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 #ifndef PSD_WS_WAITMODE
 #define PSD_WS_WAITMODE 0  // 0: try_wait with a suspend-time hint, 1: plain try_wait, 2: test_wait first, then try_wait
 #endif
-#ifndef PSD_WS_NO_VHIST
-#define PSD_WS_NO_VHIST 0
-#endif
 #ifndef PSD_WS_PAIRWAIT
 #define PSD_WS_PAIRWAIT 1  // 1: the consumer checks the FULL barriers of two consecutive frames back to back
 #endif
@@ -460,11 +457,18 @@ __device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const Ws
     constexpr bool kYH = (F & PSD_F_YHIST) != 0;
     constexpr bool kEDGE = (F & PSD_F_EDGES) != 0;
 #if PSD_WS_PAIRWAIT
-    // even frame of a body: check this frame's and the next frame's barrier back to back, so the latency of the
-    // second check hides behind the first; the odd frame then finds its data without asking again
-    if ((J & 1) == 0) {
+    // HSV pass (issue-bound), even frame of a body: check this frame's and the next frame's barrier back to back,
+    // so the latency of the second check hides behind the first; the odd frame then finds its data without asking
+    // again.  The byte-sum and histogram passes are bandwidth-bound: waiting for two stages before touching the
+    // first would halve their effective ring depth (histogram: 0.85 of the roofline against 0.95), so they wait
+    // stage by stage.
+    if (kHSV) {
+        if ((J & 1) == 0) {
+            mbar_wait_hint_off<J * 8>(ad.full, parity);
+            mbar_wait_hint_off<J * 8 + 8>(ad.full, parity);
+        }
+    } else {
         mbar_wait_hint_off<J * 8>(ad.full, parity);
-        mbar_wait_hint_off<J * 8 + 8>(ad.full, parity);
     }
 #else
     mbar_wait_hint_off<J * 8>(ad.full, parity);
@@ -498,13 +502,11 @@ __device__ __forceinline__ void ws_step(const ScoreArgs& a, WsSmem& sm, const Ws
             } else {
                 for (int p = 0; p < kPxPerThread; ++p) vp[p] = (uint8_t)(cur.v[p >> 2] >> ((p & 3) * 8));
             }
-#if !PSD_WS_NO_VHIST   // (A/B switch: what the V histogram costs; results are wrong without it)
             // bin address = histogram base + 4 * byte: one IDP4A with the weight 4 on the pixel's byte
             const uint32_t vh = smem_u32(sm.vhist[stage0 + J]);
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p)
                 red_shared_add_off<0>(__dp4a(cur.v[p >> 2], 4u << ((p & 3) * 8), vh), 1u);
-#endif
         }
     }
     if (mine) {
