@@ -30,7 +30,7 @@ def row(name, d):
     return (f"| `{name}` | {d['n_gpus']} | {d.get('scaling', '')} | {d['config'].get('frames_per_gpu', '')} x "
             f"{d['config'].get('workload', '').split(' synthetic ')[-1].split(' BGR24')[0]} | {d['value']:,.0f} | "
             f"{r.get('frac', 0):.3f} | {(e.get('value') and format(e['value'], ',.0f')) or '-'} | "
-            f"{p.get('bit_equal', p.get('within_1e-4'))}/{p.get('shard_boundaries_equal', '-')} | {c.get('sm_mhz')} {c.get('reasons')} |")
+            f"{p.get('bit_equal') if p.get('bit_equal') is not None else p.get('within_1e-4')}/{p.get('shard_boundaries_equal', '-')} | {c.get('sm_mhz')} {c.get('reasons')} |")
 
 
 def main():
@@ -38,12 +38,13 @@ def main():
     table = ["| file | GPUs | scaling | frames per GPU x size | frames/s (device-timed) | roofline frac | e2e frames/s | parity / shard boundaries | SM MHz, throttle reasons |",
              "|---|---|---|---|---|---|---|---|---|"]
     for src in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "multi_n*", "*.json*")) +
-                      glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_final", "bench*.json"))):
+                      glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_final", "bench*.json")) +
+                      glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_final", "sweep*.jsonl"))):
         ds = lines(src)
         if not ds:
             continue
         sub = os.path.basename(os.path.dirname(src))
-        dst = f"{tag}_{sub}_{os.path.basename(src)}"
+        dst = f"{sub}_{os.path.basename(src)}" if sub.startswith(tag) else f"{tag}_{sub}_{os.path.basename(src)}"
         with open(os.path.join(ROOT, "profiles", dst), "w") as f:
             for d in ds:
                 f.write(json.dumps(d) + "\n")
