@@ -489,11 +489,12 @@ def run_ours(args):
         if (sw, sh) != (W, H):   # auto-downscale: the reference's SceneManager resizes before process_frame
             from pyscenedetect_b200.scene_manager import compute_downscale_factor
             ds_factor = compute_downscale_factor(max(W, H))
-        scored = [R.downscale_frame(sample[i], ds_factor) for i in range(n_dl)] if ds_factor > 1.0 else sample
+        from oracle import ref_detectors as RD   # (`R` is the resident-ring length in this function)
+        scored = [RD.downscale_frame(sample[i], ds_factor) for i in range(n_dl)] if ds_factor > 1.0 else sample
         if rank > 0:
             halo_host = np.empty((H, W, 3), dtype=np.uint8)
             _capi.check(lib.psd_memcpy_d2h(dev, halo_host.ctypes.data, halo_t.data_ptr(), fbytes))
-            halo_host = R.downscale_frame(halo_host, ds_factor)
+            halo_host = RD.downscale_frame(halo_host, ds_factor)
             det.process_frame(first - 1, halo_host)
         t_cpu0 = time.perf_counter()
         oracle_vals, oracle_cuts = [], []
