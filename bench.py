@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps for the host-buffer e2e leg")
     ap.add_argument("--host-ring", type=int, default=256, help="distinct pinned host frames for e2e")
     ap.add_argument("--cpu-sample", type=int, default=400, help="frames in the cpu_baseline sample")
-    ap.add_argument("--edge-batch", type=int, default=1024,
+    ap.add_argument("--edge-batch", type=int, default=2048,
                     help="frames per engine batch when the Canny/dilate edge component is on (its per-pixel "
                          "scratch - V plane, class map, union-find labels - is 6 B/px per frame of a batch)")
     ap.add_argument("--no-e2e", action="store_true")
