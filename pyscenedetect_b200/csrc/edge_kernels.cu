@@ -9,11 +9,11 @@
 //
 // Everything after the gradient stage works on BIT-PACKED maps (32 pixels per word, bit i of word
 // (y, wq) = pixel 32 wq + i; padding bits are 0), 1/8 byte per pixel and plane:
-//   thresholds (V histogram of the fused pass)
+//   thresholds (V histogram of the fused pass)                                   [1 launch]
 //   -> classify: Sobel / L1 magnitude / NMS / double threshold straight into two bit planes,
-//      E = strong pixels, C = candidates (weak or strong)                       [1 launch]
+//      E = strong pixels, C = candidates (weak or strong), both tile-major      [1 launch]
 //   -> hysteresis: E grows inside C until nothing changes, bit-parallel          [1 cooperative launch]
-//   -> separable k x k max on the bits, popcount SAD against the previous frame  [3 launches]
+//   -> k x k max on the bits in one pass, popcount SAD against the previous frame [2 launches]
 // (the first version kept a byte class map, 4-byte union-find labels per pixel and 12 launches per
 // batch: profiles/r01w_launches_content_edges_summary.txt).
 #include <cooperative_groups.h>

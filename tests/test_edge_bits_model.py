@@ -1,8 +1,11 @@
-"""CPU restatement of the bit-plane edge path (csrc/edge_kernels.cu), instruction-level where the bit
-manipulation is the risk:
+"""CPU restatement of the bit-plane edge path (csrc/edge_kernels.cu, csrc/canny_pairs.cuh), instruction-level where
+the bit manipulation is the risk:
 
-  * classify: per-strip horizontal sums h = V(i-1)+2V(i)+V(i+1), c = V(i+1)-V(i-1) (the two IDP4A), vertical
-    Sobel from them, zeroed outside the image, 2-bit direction sectors, byte-per-8-columns bit planes;
+  * classify, integer form (`classify_bits`): per-strip horizontal sums h = V(i-1)+2V(i)+V(i+1), c = V(i+1)-V(i-1),
+    vertical Sobel from them, zeroed outside the image, 2-bit direction sectors, byte-per-8-columns bit planes;
+  * classify, the kernel's own arithmetic (`classify_pairs`): binary16 lanes holding n * 2^-19, the PRMT selectors
+    that build them, the sign-mask sectors from two FP32 FMAs, `p > max(p(left), m(right), low + 1)` suppression,
+    IDP.2A byte packing - must equal the integer form, cv2.Sobel and cv2.Canny;
   * hysteresis: 64x32 tiles, rows as 64-bit words, `run_fill` with the two carry walks, the one-pixel ring
     taken from the neighbouring tiles, rounds until no tile changes.
 
