@@ -339,6 +339,10 @@ int psd_engine_create(const psd_config* cfg, psd_engine** out) {
             k = 4 + (int)nearbyint(sqrt((double)e->W * (double)e->H) / 192.0);
             if ((k & 1) == 0) k += 1;
         }
+        if (k > 63) {  // the bit-plane dilation shifts words by at most 31 bits
+            psd_engine_destroy(e);
+            PSD_REQUIRE(false, "edge kernel size %d is not supported (odd sizes 3 .. 63)", k);
+        }
         e->ksize = k;
     }
     if (e->features & PSD_F_HASH) {

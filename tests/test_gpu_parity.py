@@ -280,6 +280,31 @@ def test_edge_intermediates_match_cv2(lib, shape):
     eng.close()
 
 
+@pytest.mark.parametrize("k", [3, 9, 17, 19, 25])
+def test_edge_dilation_kernel_sizes(lib, k):
+    """Explicit dilation kernel sizes: k <= 17 runs the register-ring kernel (R = 1 .. 8), larger k (the estimate for
+    4K frames is 19) the one-thread-per-word kernel; dilated map and edge SAD vs cv2.dilate."""
+    from pyscenedetect_b200.engine import F_EDGES, Engine
+    from pyscenedetect_b200.synth import ScenePlan, render_frames
+    w, h = 200, 90
+    frames = render_frames(ScenePlan(10, seed=6, min_len=4, max_len=6).params, w, h)
+    eng = Engine(w, h, F_EDGES, max_batch=4, edge_kernel_size=k)   # several sub-batches: the carry plane is used
+    assert eng.edge_kernel_size == k
+    kernel = np.ones((k, k), np.uint8)
+    prev = None
+    for b in range(0, len(frames), 4):
+        eng.submit(frames[b:b + 4])
+        sums = eng.read_sums(b, min(4, len(frames) - b))
+        for j, f in enumerate(frames[b:b + 4]):
+            lum = cv2.split(cv2.cvtColor(f, cv2.COLOR_BGR2HSV))[2]
+            want = R.detect_edges(lum, kernel)
+            assert np.array_equal(eng.debug_plane(3, j), want), (k, b + j)
+            if prev is not None:
+                assert int(sums["sad_edges"][j]) == M.sad(want, prev), (k, b + j)
+            prev = want
+    eng.close()
+
+
 def test_edge_path_matches_cv2_at_1080p(lib):
     """BASELINE.json configs[2] size: Canny map, dilated edges and the edge SAD of 1920x1080 frames vs cv2
     (30 x 34 hysteresis tiles, k = 13, components spanning many tiles).  The blurred-noise frames are dense
